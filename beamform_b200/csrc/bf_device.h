@@ -1,0 +1,60 @@
+// Host<->device parameter block shared by capi.cu and the kernels.  Plain data only.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace bf {
+
+enum { ALGO_DAS = 0, ALGO_MVDR = 1, ALGO_LCMV = 2, ALGO_GSS = 3, ALGO_PHASE = 4, ALGO_PHASEMPF = 5 };
+
+// "Logical bins": the reference loops over all N FFT bins (das.cpp:60); inputs are real so bin N-j is
+// the conjugate of bin j and every per-bin rule is conjugate-equivariant EXCEPT at the pair
+// (N/2-1, N/2+1), whose frequencies differ (util.h:198, SURVEY B-1..B-4).  The kernels therefore
+// process l = 0..N/2 plus one pseudo-bin l = N/2+1 (input = conj of bin N/2-1, own steering, own state).
+// All per-bin tables are indexed by l in [0, N/2+2).
+struct KernelParams {
+  // ---- I/O (floats; strides in floats) ----
+  const float* in;
+  long long in_stream_stride, in_mic_stride;
+  float* out;
+  long long out_stream_stride;
+  int n_streams, M, H, N;
+  int hop_begin, hop_end;   // this launch processes hops [hop_begin, hop_end) of the arrays above
+  int frame_index0;         // global frame counter of hop 0 of this call (history / MCRA bookkeeping)
+  // ---- per-stream state carried between launches / calls ----
+  float* prev_hop;          // [B][M][H]  the hop before hop 0 of this call (zeros at start: util.h:275-277)
+  float* tail;              // [B][H]     second half of the last synthesised frame (out_buff[0], util.h:301-302)
+  // ---- tables ----
+  const float2* steer;      // [L][C][M]  weights[j](i,k): steering vectors, look direction k=0, interferers k>=1
+  const float2* das_ceff;   // [M][N]     DAS only: Hermitian-ised effective weights (see capi.cu: build_das_ceff)
+  const uint8_t* inband;    // [L]        freq_min <= |freqs[j]| <= freq_max (mvdr.cpp:84)
+  int C;                    // K+1 columns of the steering matrix
+  float out_scale;          // out_amp / N
+  // ---- diagnostics ----
+  uint8_t* capture;         // [B][n_hops_call][N] or null
+  long long capture_stream_stride;
+  // ---- algorithm parameters (float copies of bf_config) ----
+  float thr_mag;            // freq_mag_threshold * M * N   (gate compares sum_i |X_i| directly)
+  double thr_mag_d;         // exact double threshold for the FP64 recheck
+  int P;                    // past_windows
+  float2* hist;             // [B][Lsel][P][M]  mvdr/lcmv history ring, slot = frame % P
+  const int* sel_slot;      // [L] -> slot in the in-band compact list or -1
+  int Lsel;
+  float mu, lambda_mu;      // gss: mu, (1 - lambda*mu)
+  float2* gss_w;            // [B][Lsel][C][M]
+  float gss_dj2_scale;      // 2 * (1/(K+1)) in integer arithmetic (gss.cpp:133) -> 2 for K=0 else 0
+  float min_phase_rad, mag_mult, thr_phase_mag;   // phase
+  float min_mag;            // phasempf
+  const double* win_d;      // [N] sqrt-hann in double, for FP64 rechecks
+  const double2* twid_d;    // [N] e^{-2 pi i k/N} in double, for FP64 rechecks
+  // phasempf state, [B][7][L] floats: S_prev, S_tmp, S_min, lambda_noise, Z, rev0, rev1
+  float* mpf_state;
+  float mcra_alphaS, mcra_alphaD, mcra_alphaD2, mcra_delta;
+  int mcra_L, mcra_cur_L0, mcra_first0;   // counters at hop_begin (advance deterministically per frame)
+  float mpf_alphaS, mpf_eta, mpf_gamma, mpf_rev_gain, out_amp, noise_floor;
+  int out_only_noise, out_only_mcra;
+  int smooth_size;
+  float* smooth_hist;       // [B][smooth_size-1] last OLA samples before hop 0 of this call
+};
+
+}   // namespace bf

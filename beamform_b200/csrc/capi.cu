@@ -1,0 +1,571 @@
+// C ABI + host runtime of beamform_b200 (see include/beamform_b200.h).
+//
+// Host side of the drop-in boundary: configuration ingest (util.h:52-134 + <algo>_handle_params),
+// geometry -> delays -> steering tables in double (util.h:136-199, das.cpp:27-45 and its five copies),
+// the /theta and /theta_interference state machine (lcmv.cpp:258-309), event-segmented launches of the
+// fused CUDA kernels, and per-stream state.  There is no CPU compute path: every sample goes through the
+// sm_100a kernels in frames_kernel.cu.  Citations are relative to /root/reference/beamform/src/.
+#include <algorithm>
+#include <cmath>
+#include <complex>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <map>
+#include <mutex>
+#include <sstream>
+#include <string>
+#include <vector>
+
+#include "../../include/beamform_b200.h"
+#include "bf_device.h"
+
+namespace bf {
+cudaError_t launch_frames_kernel_1024(int algo, const KernelParams& p, cudaStream_t st);
+cudaError_t launch_save_prev_hop(const KernelParams& p, int last_hop, cudaStream_t st);
+size_t frames_kernel_smem(int M);
+}   // namespace bf
+
+typedef std::complex<double> cd;
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+#define CUDA_TRY(x)                                                                                  \
+  do {                                                                                               \
+    cudaError_t e_ = (x);                                                                            \
+    if (e_ != cudaSuccess) return fail(BF_ERR_CUDA, std::string(#x) + ": " + cudaGetErrorString(e_)); \
+  } while (0)
+
+// util.h:23-27
+static const double kPi = 3.141592653589793238462643383279502884;
+static const double kVSound = 343;
+static const double kRad2Deg = 180.0 / kPi;
+static const double kDeg2Rad = kPi / 180.0;
+
+struct PendingEvent {
+  int kind;
+  uint16_t id;
+  float value;
+};
+
+struct bf_handle {
+  bf_config cfg;
+  uint32_t B = 0, M = 0, H = 0, N = 0, L = 0;
+  int dev = 0;
+  cudaStream_t own_stream = nullptr;
+  // ---- reference globals (util.h:31-36) ----
+  double angle = 0;
+  std::vector<double> mic_dist, mic_angle;
+  std::vector<double> interference_angles;
+  std::vector<double> freqs;
+  // weights[j](i,k): [N][M][C]; row-0 semantics of update_weights(ini) are kept (SURVEY B-8)
+  std::vector<cd> weights;
+  int C = 1;
+  // ---- device ----
+  float* d_prev_hop = nullptr;
+  float* d_tail = nullptr;
+  float2* d_steer = nullptr;
+  float2* d_das_ceff = nullptr;
+  uint8_t* d_inband = nullptr;
+  uint8_t* d_capture = nullptr;
+  size_t steer_cap = 0;
+  // hop-at-a-time staging
+  float* h_stage_in = nullptr;
+  float* h_stage_out = nullptr;
+  float* d_stage_in = nullptr;
+  float* d_stage_out = nullptr;
+  // ---- bookkeeping ----
+  uint64_t frames_done = 0;
+  uint64_t launches = 0;
+  int drop_left = 0;
+  bool tables_dirty = true;
+  std::mutex mtx;
+  std::vector<PendingEvent> pending;
+};
+
+// ------------------------------------------------------------------------------------------------
+// configuration
+// ------------------------------------------------------------------------------------------------
+extern "C" int bf_config_init(bf_config* c, int algo) {
+  if (!c || algo < 0 || algo > 5) return fail(BF_ERR_INVALID, "bf_config_init: bad arguments");
+  memset(c, 0, sizeof(*c));
+  c->algo = algo;
+  c->sample_rate = 48000;   // rosjack_config.yaml:9 (JACK decides at run time)
+  c->hop = 512;
+  c->initial_angle = 0.0;   // util.h:71
+  // getParam fall-backs: mvdr.cpp:155-184, lcmv.cpp:179-216, gss.cpp:186-237
+  c->past_windows = 10;
+  c->freq_mag_threshold = 1.5;
+  c->freq_max = 4000;
+  c->freq_min = 400;
+  c->out_amp = (algo == BF_ALGO_PHASEMPF) ? 2.0 : 4.5;   // phasempf.cpp:451
+  c->interf_angle_threshold = 5.0;
+  c->mu = 0.01;      // gss.cpp fall-back
+  c->lambda = 0.0;
+  // phase.cpp:170-189
+  c->min_phase = 10.0;
+  c->mag_mult = 0.1;
+  c->mag_threshold = 0.05;
+  // phasempf.cpp:361-470 (fall-backs, not the global initialisers; SURVEY B-11)
+  c->min_mag = 10.0;
+  c->smooth_size = 20;
+  c->MCRA_alphaS = 0.95; c->MCRA_alphaD = 0.95; c->MCRA_alphaD2 = 0.97; c->MCRA_delta = 0.001;
+  c->MCRA_L = 0;     // "MCRA_L = 0.01" assigned to an int (phasempf.cpp:416)
+  c->MPF_alphaS = 0.3; c->MPF_eta = 0.3; c->MPF_rev_gamma = 0.3; c->MPF_rev_delta = 1.0;
+  c->noise_floor = 0.001;
+  c->out_only_noise = 0; c->out_only_mcra = 0;
+  c->dropped_hops_on_restructure = 0;
+  c->device = 0;
+  return BF_OK;
+}
+
+static std::string trim(const std::string& s) {
+  size_t a = s.find_first_not_of(" \t\r\n"), b = s.find_last_not_of(" \t\r\n");
+  return a == std::string::npos ? std::string() : s.substr(a, b - a + 1);
+}
+static bool parse_bool(const std::string& v) { return v == "true" || v == "True" || v == "1"; }
+
+extern "C" int bf_config_set(bf_config* c, const char* key_c, const char* val_c) {
+  if (!c || !key_c || !val_c) return fail(BF_ERR_INVALID, "bf_config_set: null argument");
+  const std::string key = trim(key_c), val = trim(val_c);
+  const double v = atof(val.c_str());
+#define KEYD(name) if (key == #name) { c->name = v; return BF_OK; }
+  KEYD(freq_mag_threshold) KEYD(freq_max) KEYD(freq_min) KEYD(out_amp) KEYD(interf_angle_threshold) KEYD(mu) KEYD(lambda)
+  KEYD(min_phase) KEYD(mag_mult) KEYD(mag_threshold) KEYD(min_mag) KEYD(MCRA_alphaS) KEYD(MCRA_alphaD) KEYD(MCRA_alphaD2)
+  KEYD(MCRA_delta) KEYD(MPF_alphaS) KEYD(MPF_eta) KEYD(MPF_rev_gamma) KEYD(MPF_rev_delta) KEYD(noise_floor)
+  KEYD(initial_angle) KEYD(sample_rate)
+#undef KEYD
+  if (key == "past_windows") { c->past_windows = (uint32_t)(int)v; return BF_OK; }   // mvdr.cpp:152 (int) cast
+  if (key == "smooth_size") { c->smooth_size = (int)v < 1 ? 20 : (int)v; return BF_OK; }   // phasempf.cpp:377-381
+  if (key == "MCRA_L") { c->MCRA_L = (int)v; return BF_OK; }
+  if (key == "hop" || key == "period") { c->hop = (uint32_t)v; return BF_OK; }
+  if (key == "out_only_noise") { c->out_only_noise = parse_bool(val); return BF_OK; }
+  if (key == "out_only_mcra") { c->out_only_mcra = parse_bool(val); return BF_OK; }
+  if (key == "dropped_hops_on_restructure") { c->dropped_hops_on_restructure = (int)v; return BF_OK; }
+  if (key == "device") { c->device = (int)v; return BF_OK; }
+  // keys a node never reads are ignored, exactly like an unused ROS parameter (SURVEY B-11:
+  // phase.launch sets min_mag / smooth_size, which phase.cpp does not read)
+  return BF_OK;
+}
+
+// beamform_config.yaml subset: scalars and one-line flow maps "micN: {id: .., x: .., y: ..[, z: ..]}".
+extern "C" int bf_config_load_yaml(bf_config* c, const char* path) {
+  if (!c || !path) return fail(BF_ERR_INVALID, "bf_config_load_yaml: null argument");
+  std::ifstream f(path);
+  if (!f) return fail(BF_ERR_IO, std::string("cannot open ") + path);
+  std::map<int, std::pair<double, double> > mics;
+  std::map<int, double> interf;
+  std::string line;
+  while (std::getline(f, line)) {
+    size_t hash = line.find('#');
+    if (hash != std::string::npos) line = line.substr(0, hash);
+    size_t colon = line.find(':');
+    if (colon == std::string::npos) continue;
+    std::string key = trim(line.substr(0, colon)), val = trim(line.substr(colon + 1));
+    if (key.empty()) continue;
+    if (key.compare(0, 3, "mic") == 0 && key.size() > 3 && isdigit((unsigned char)key[3]) && !val.empty() && val[0] == '{') {
+      int idx = atoi(key.c_str() + 3);
+      double x = 0, y = 0;
+      std::string body = val.substr(1, val.find('}') == std::string::npos ? std::string::npos : val.find('}') - 1);
+      std::stringstream ss(body);
+      std::string item;
+      while (std::getline(ss, item, ',')) {
+        size_t c2 = item.find(':');
+        if (c2 == std::string::npos) continue;
+        std::string k = trim(item.substr(0, c2));
+        double vv = atof(trim(item.substr(c2 + 1)).c_str());
+        if (k == "x") x = vv;
+        if (k == "y") y = vv;   // z is ignored by the reference as well (SURVEY B-6)
+      }
+      mics[idx] = std::make_pair(x, y);
+    } else if (key.compare(0, 12, "angle_interf") == 0) {
+      interf[atoi(key.c_str() + 12)] = atof(val.c_str());
+    } else if (key == "initial_angle") {
+      c->initial_angle = atof(val.c_str());
+    } else {
+      bf_config_set(c, key.c_str(), val.c_str());
+    }
+  }
+  // util.h:82-92: micN are read until the first missing index
+  c->n_mics = 0;
+  for (int i = 0; i < BF_MAX_MICS; i++) {
+    auto it = mics.find(i);
+    if (it == mics.end()) break;
+    c->mic_x[i] = it->second.first;
+    c->mic_y[i] = it->second.second;
+    c->n_mics = i + 1;
+  }
+  // util.h:94-113: angle_interfK are read until the first missing one or the first |a| > 180;
+  // the cut is re-applied in bf_create so raw arrays behave the same.
+  c->n_angle_interf = 0;
+  for (int k = 1; k <= BF_MAX_INTERF; k++) {
+    auto it = interf.find(k);
+    if (it == interf.end()) break;
+    c->angle_interf[k - 1] = it->second;
+    c->n_angle_interf = k;
+  }
+  return BF_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// geometry, frequency vector, steering (all double, as the reference)
+// ------------------------------------------------------------------------------------------------
+static void calculate_delays(const bf_handle* h, double look, double* delay) {   // util.h:136-188
+  for (uint32_t i = 0; i < h->M; i++) {
+    if (i == 0) { delay[i] = 0.0; continue; }
+    double a = h->mic_angle[i] - look;
+    if (a > 180) a -= 360;
+    else if (a < -180) a += 360;
+    delay[i] = h->mic_dist[i] * std::cos(a * kDeg2Rad) / (-kVSound);
+  }
+}
+
+static void calculate_frequency_vector(bf_handle* h) {   // util.h:190-199
+  const uint32_t N = h->N;
+  h->freqs.assign(N, 0.0);   // [N/2] is never written by the reference: pinned to 0.0 (SURVEY B-2)
+  for (uint32_t i = 0; i < N / 2 - 1; ++i) {
+    h->freqs[i + 1] = ((double)(i + 1) / (double)N) * h->cfg.sample_rate;
+    h->freqs[N - 1 - i] = -((double)(i + 1) / (double)N) * h->cfg.sample_rate;
+  }
+  h->freqs[N / 2 - 1] = h->cfg.sample_rate / 2;   // util.h:198 (SURVEY B-1)
+}
+
+static inline cd& W(bf_handle* h, uint32_t j, uint32_t i, int k) { return h->weights[((size_t)j * h->M + i) * h->C + k]; }
+
+// lcmv.cpp:221-256: buffers are re-created zero-filled whenever the interferer count changes
+static void allocate_interf_buffers(bf_handle* h) {
+  h->C = (int)h->interference_angles.size() + 1;
+  h->weights.assign((size_t)h->N * h->M * h->C, cd(0, 0));
+}
+
+// das.cpp:27-45 / lcmv.cpp:44-86: row 0 is only written when ini (SURVEY B-8)
+static void update_weights(bf_handle* h, bool ini) {
+  std::vector<double> delay(h->M);
+  for (int k = 0; k < h->C; k++) {
+    calculate_delays(h, k == 0 ? h->angle : h->interference_angles[k - 1], delay.data());
+    for (uint32_t i = 0; i < h->M; i++) {
+      if (i == 0) {
+        if (ini)
+          for (uint32_t j = 0; j < h->N; j++) W(h, j, 0, k) = 1.0;
+      } else {
+        for (uint32_t j = 0; j < h->N; j++) W(h, j, i, k) = std::exp(-cd(0, 1) * (double)2 * kPi * h->freqs[j] * delay[i]);
+      }
+    }
+  }
+  h->tables_dirty = true;
+}
+
+static uint32_t bin_of_logical(const bf_handle* h, uint32_t l) { return l; }   // l = N/2+1 is FFT bin N/2+1 itself
+
+static int upload_tables(bf_handle* h, cudaStream_t st) {
+  if (!h->tables_dirty) return BF_OK;
+  const uint32_t N = h->N, M = h->M, L = h->L;
+  const size_t nsteer = (size_t)L * h->C * M;
+  if (nsteer > h->steer_cap) {
+    if (h->d_steer) cudaFree(h->d_steer);
+    CUDA_TRY(cudaMalloc(&h->d_steer, sizeof(float2) * nsteer));
+    h->steer_cap = nsteer;
+  }
+  std::vector<float2> steer(nsteer);
+  for (uint32_t l = 0; l < L; l++)
+    for (int k = 0; k < h->C; k++)
+      for (uint32_t i = 0; i < M; i++) {
+        cd w = W(h, bin_of_logical(h, l), i, k);
+        steer[((size_t)l * h->C + k) * M + i] = make_float2((float)w.real(), (float)w.imag());
+      }
+  CUDA_TRY(cudaMemcpyAsync(h->d_steer, steer.data(), sizeof(float2) * nsteer, cudaMemcpyHostToDevice, st));
+  if (h->cfg.algo == BF_ALGO_DAS) {
+    // Y[j] = (1/M) sum_i conj(w_ij) X_i[j] (das.cpp:60-63), out = Re(IFFT(Y)) (util.h:249).  Re() keeps the
+    // Hermitian part Yh[j] = (Y[j] + conj(Y[N-j]))/2 = ceff_i[j] X_i[j] with
+    // ceff_i[j] = (conj(w_ij) + w_i,N-j)/(2M): exactly Hermitian, so two frames can share one complex inverse.
+    std::vector<float2> ceff((size_t)M * N);
+    for (uint32_t i = 0; i < M; i++)
+      for (uint32_t j = 0; j < N; j++) {
+        cd a = std::conj(W(h, j, i, 0)), b = W(h, (N - j) % N, i, 0);
+        cd c = (a + b) / (2.0 * M);
+        ceff[(size_t)i * N + j] = make_float2((float)c.real(), (float)c.imag());
+      }
+    CUDA_TRY(cudaMemcpyAsync(h->d_das_ceff, ceff.data(), sizeof(float2) * ceff.size(), cudaMemcpyHostToDevice, st));
+  }
+  std::vector<uint8_t> inband(L);
+  for (uint32_t l = 0; l < L; l++) {
+    double f = std::fabs(h->freqs[bin_of_logical(h, l)]);   // mvdr.cpp:78,84
+    inband[l] = (f >= h->cfg.freq_min && f <= h->cfg.freq_max) ? 1 : 0;
+  }
+  CUDA_TRY(cudaMemcpyAsync(h->d_inband, inband.data(), L, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaStreamSynchronize(st));   // host vectors go out of scope
+  h->tables_dirty = false;
+  return BF_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// lifecycle
+// ------------------------------------------------------------------------------------------------
+extern "C" int bf_create(bf_handle** out, const bf_config* cfg, uint32_t n_streams) {
+  if (!out || !cfg) return fail(BF_ERR_INVALID, "bf_create: null argument");
+  *out = nullptr;
+  if (cfg->n_mics < 1 || cfg->n_mics > BF_MAX_MICS) return fail(BF_ERR_INVALID, "bf_create: n_mics must be in [1, 64]");
+  if (n_streams < 1) return fail(BF_ERR_INVALID, "bf_create: n_streams must be >= 1");
+  if (cfg->hop != 512) return fail(BF_ERR_INVALID, "bf_create: this build supports hop 512 (1024-point frames) only");
+  if (cfg->algo < 0 || cfg->algo > 5) return fail(BF_ERR_INVALID, "bf_create: unknown algo");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1 || cfg->device >= ndev)
+    return fail(BF_ERR_NO_DEVICE, "bf_create: no CUDA device (beamform_b200 has no CPU path)");
+  cudaDeviceProp prop;
+  CUDA_TRY(cudaGetDeviceProperties(&prop, cfg->device));
+  if (prop.major != 10) return fail(BF_ERR_NO_DEVICE, "bf_create: kernels are built for sm_100a only");
+  CUDA_TRY(cudaSetDevice(cfg->device));
+
+  bf_handle* h = new bf_handle();
+  h->cfg = *cfg;
+  h->dev = cfg->device;
+  h->B = n_streams; h->M = cfg->n_mics; h->H = cfg->hop; h->N = 2 * cfg->hop; h->L = h->N / 2 + 2;
+  // util.h:82-92,116-119: polar coordinates from the RAW positions; the later mic0 re-referencing of x,y
+  // never feeds back into dist/angle (SURVEY B-6), so only the raw values matter.
+  for (uint32_t i = 0; i < h->M; i++) {
+    h->mic_dist.push_back(std::sqrt(cfg->mic_x[i] * cfg->mic_x[i] + cfg->mic_y[i] * cfg->mic_y[i]));
+    h->mic_angle.push_back(std::atan2(cfg->mic_y[i], cfg->mic_x[i]) * kRad2Deg);
+  }
+  h->angle = cfg->initial_angle;
+  if (cfg->algo == BF_ALGO_LCMV || cfg->algo == BF_ALGO_GSS) {
+    for (int k = 0; k < cfg->n_angle_interf && k < BF_MAX_INTERF; k++) {   // util.h:101-112
+      if (std::fabs(cfg->angle_interf[k]) <= 180) h->interference_angles.push_back(cfg->angle_interf[k]);
+      else break;
+    }
+  }
+  calculate_frequency_vector(h);
+  allocate_interf_buffers(h);
+  update_weights(h, true);
+
+  cudaError_t e = cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking);
+  if (e != cudaSuccess) { delete h; return fail(BF_ERR_CUDA, cudaGetErrorString(e)); }
+  const size_t prev_n = (size_t)h->B * h->M * h->H, tail_n = (size_t)h->B * h->H;
+  bool ok = cudaMalloc(&h->d_prev_hop, sizeof(float) * prev_n) == cudaSuccess &&
+            cudaMalloc(&h->d_tail, sizeof(float) * tail_n) == cudaSuccess &&
+            cudaMalloc(&h->d_inband, h->L) == cudaSuccess &&
+            cudaMalloc(&h->d_das_ceff, sizeof(float2) * h->M * h->N) == cudaSuccess &&
+            cudaMalloc(&h->d_stage_in, sizeof(float) * h->M * h->H) == cudaSuccess &&
+            cudaMalloc(&h->d_stage_out, sizeof(float) * h->H) == cudaSuccess &&
+            cudaMallocHost(&h->h_stage_in, sizeof(float) * h->M * h->H) == cudaSuccess &&
+            cudaMallocHost(&h->h_stage_out, sizeof(float) * h->H) == cudaSuccess;
+  if (!ok) { bf_destroy(h); return fail(BF_ERR_ALLOC, "bf_create: device allocation failed"); }
+  cudaMemset(h->d_prev_hop, 0, sizeof(float) * prev_n);   // util.h:275-277: one hop of zeros pre-loaded
+  cudaMemset(h->d_tail, 0, sizeof(float) * tail_n);       // util.h:285: calloc'ed out_buff
+  int rc = upload_tables(h, h->own_stream);
+  if (rc != BF_OK) { bf_destroy(h); return rc; }
+  *out = h;
+  return BF_OK;
+}
+
+extern "C" void bf_destroy(bf_handle* h) {
+  if (!h) return;
+  cudaSetDevice(h->dev);
+  if (h->own_stream) { cudaStreamSynchronize(h->own_stream); cudaStreamDestroy(h->own_stream); }
+  cudaFree(h->d_prev_hop); cudaFree(h->d_tail); cudaFree(h->d_steer); cudaFree(h->d_das_ceff); cudaFree(h->d_inband);
+  cudaFree(h->d_stage_in); cudaFree(h->d_stage_out);
+  if (h->h_stage_in) cudaFreeHost(h->h_stage_in);
+  if (h->h_stage_out) cudaFreeHost(h->h_stage_out);
+  delete h;
+}
+
+// ------------------------------------------------------------------------------------------------
+// control topics
+// ------------------------------------------------------------------------------------------------
+static void apply_theta(bf_handle* h, float data) {   // das.cpp:94-99
+  h->angle = data;
+  update_weights(h, false);
+}
+
+// lcmv.cpp:258-309 == gss.cpp:288-339.  Returns 1 when the list was restructured.
+static int apply_interference(bf_handle* h, uint16_t id, float msg_angle) {
+  std::vector<double>& ia = h->interference_angles;
+  int restructured = 0;
+  if (id >= 1 && id <= ia.size()) {
+    ia[id - 1] = msg_angle;
+    for (int i = 0; i < (int)ia.size(); i++) {
+      if (i != (id - 1) && std::fabs(ia[i] - msg_angle) < h->cfg.interf_angle_threshold) {
+        ia.erase(ia.begin() + id - 1);
+        allocate_interf_buffers(h);
+        restructured = 1;
+        break;
+      }
+    }
+    update_weights(h, false);
+  } else if (id > ia.size()) {
+    int i;
+    for (i = 0; i < (int)ia.size(); i++)
+      if (std::fabs(ia[i] - msg_angle) < h->cfg.interf_angle_threshold) break;
+    if (i == (int)ia.size() && ia.size() < BF_MAX_INTERF) {
+      ia.push_back(msg_angle);
+      allocate_interf_buffers(h);
+      restructured = 1;
+      update_weights(h, false);
+    }
+  }   // id == 0: "Invalid interference id" (lcmv.cpp:306-308): no change
+  return restructured;
+}
+
+static void apply_event(bf_handle* h, int kind, uint32_t id, float value) {
+  if (kind == 0) {
+    apply_theta(h, value);
+  } else if (h->cfg.algo == BF_ALGO_LCMV || h->cfg.algo == BF_ALGO_GSS) {   // only lcmv/gss subscribe (lcmv.cpp:320)
+    if (apply_interference(h, (uint16_t)id, value)) h->drop_left = h->cfg.dropped_hops_on_restructure;
+  }
+}
+
+extern "C" int bf_set_theta(bf_handle* h, float angle_deg) {
+  if (!h) return fail(BF_ERR_INVALID, "null handle");
+  std::lock_guard<std::mutex> lk(h->mtx);
+  h->pending.push_back(PendingEvent{0, 0, angle_deg});
+  return BF_OK;
+}
+extern "C" int bf_set_interference(bf_handle* h, uint16_t id, float angle_deg) {
+  if (!h) return fail(BF_ERR_INVALID, "null handle");
+  std::lock_guard<std::mutex> lk(h->mtx);
+  h->pending.push_back(PendingEvent{1, id, angle_deg});
+  return BF_OK;
+}
+static void drain_pending(bf_handle* h) {
+  std::vector<PendingEvent> ev;
+  {
+    std::lock_guard<std::mutex> lk(h->mtx);
+    ev.swap(h->pending);
+  }
+  for (const PendingEvent& e : ev) apply_event(h, e.kind, e.id, e.value);
+}
+extern "C" int bf_get_theta(bf_handle* h, double* a) {
+  if (!h || !a) return fail(BF_ERR_INVALID, "null argument");
+  drain_pending(h);
+  *a = h->angle;
+  return BF_OK;
+}
+extern "C" int bf_get_interferences(bf_handle* h, double* angles, uint32_t cap, uint32_t* n) {
+  if (!h || !n) return fail(BF_ERR_INVALID, "null argument");
+  drain_pending(h);
+  *n = (uint32_t)h->interference_angles.size();
+  for (uint32_t i = 0; i < *n && i < cap && angles; i++) angles[i] = h->interference_angles[i];
+  return BF_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// processing
+// ------------------------------------------------------------------------------------------------
+__global__ void zero_hops_kernel(float* out, long long stride, int n) {
+  float* o = out + (size_t)blockIdx.x * stride;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) o[i] = 0.0f;
+}
+
+static int run_segment(bf_handle* h, const float* in, size_t ss, size_t ms, float* out, size_t os, uint32_t h0, uint32_t h1,
+                       uint32_t call_hops, cudaStream_t st) {
+  if (h1 <= h0) return BF_OK;
+  int rc = upload_tables(h, st);
+  if (rc != BF_OK) return rc;
+  bf::KernelParams p;
+  memset(&p, 0, sizeof(p));
+  p.in = in + (size_t)h0 * h->H;
+  p.in_stream_stride = (long long)ss; p.in_mic_stride = (long long)ms;
+  p.out = out + (size_t)h0 * h->H;
+  p.out_stream_stride = (long long)os;
+  p.n_streams = h->B; p.M = h->M; p.H = h->H; p.N = h->N;
+  p.hop_begin = 0; p.hop_end = (int)(h1 - h0);
+  p.frame_index0 = (int)(h->frames_done & 0x7fffffff);
+  p.prev_hop = h->d_prev_hop; p.tail = h->d_tail;
+  p.steer = h->d_steer; p.das_ceff = h->d_das_ceff; p.inband = h->d_inband; p.C = h->C;
+  const bool amp = h->cfg.algo == BF_ALGO_MVDR || h->cfg.algo == BF_ALGO_LCMV || h->cfg.algo == BF_ALGO_GSS;
+  p.out_scale = (float)((amp ? h->cfg.out_amp : 1.0) / (double)h->N);
+  if (h->d_capture) {
+    p.capture = h->d_capture + (size_t)h0 * h->N;
+    p.capture_stream_stride = (long long)call_hops * h->N;
+  }
+  CUDA_TRY(bf::launch_frames_kernel_1024(h->cfg.algo, p, st));
+  CUDA_TRY(bf::launch_save_prev_hop(p, (int)(h1 - h0) - 1, st));
+  h->launches += 2;
+  h->frames_done += h1 - h0;
+  return BF_OK;
+}
+
+extern "C" int bf_process_batch_device(bf_handle* h, const float* in, size_t ss, size_t ms, float* out, size_t os, uint32_t n_hops,
+                                       const bf_event* ev, uint32_t n_ev, void* cuda_stream) {
+  if (!h || !in || !out) return fail(BF_ERR_INVALID, "bf_process_batch_device: null argument");
+  CUDA_TRY(cudaSetDevice(h->dev));
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  drain_pending(h);
+  uint32_t e = 0, t = 0;
+  while (t < n_hops) {
+    while (e < n_ev && ev[e].hop_index <= t) { apply_event(h, ev[e].kind, ev[e].id, ev[e].value); e++; }
+    if (h->drop_left > 0) {
+      // READY=false: the callback emits zeros and does not feed the ring buffers (lcmv.cpp:148-155)
+      uint32_t nd = std::min<uint32_t>((uint32_t)h->drop_left, n_hops - t);
+      zero_hops_kernel<<<h->B, 256, 0, st>>>(out + (size_t)t * h->H, (long long)os, (int)(nd * h->H));
+      h->launches++;
+      h->drop_left -= (int)nd;
+      t += nd;
+      continue;
+    }
+    uint32_t t1 = (e < n_ev) ? std::min<uint32_t>(ev[e].hop_index, n_hops) : n_hops;
+    if (t1 <= t) t1 = t + 1;
+    int rc = run_segment(h, in, ss, ms, out, os, t, t1, n_hops, st);
+    if (rc != BF_OK) return rc;
+    t = t1;
+  }
+  while (e < n_ev) { apply_event(h, ev[e].kind, ev[e].id, ev[e].value); e++; }   // events at/after the end
+  return BF_OK;
+}
+
+extern "C" int bf_process_batch(bf_handle* h, const float* in_host, size_t ss, size_t ms, float* out_host, size_t os,
+                                uint32_t n_hops, const bf_event* ev, uint32_t n_ev) {
+  if (!h || !in_host || !out_host) return fail(BF_ERR_INVALID, "bf_process_batch: null argument");
+  CUDA_TRY(cudaSetDevice(h->dev));
+  const size_t L = (size_t)n_hops * h->H;
+  float *d_in = nullptr, *d_out = nullptr;
+  CUDA_TRY(cudaMalloc(&d_in, sizeof(float) * h->B * h->M * L));
+  if (cudaMalloc(&d_out, sizeof(float) * h->B * L) != cudaSuccess) { cudaFree(d_in); return fail(BF_ERR_ALLOC, "bf_process_batch: alloc"); }
+  cudaStream_t st = h->own_stream;
+  // gather each (stream, mic) row into a dense [B][M][L] device tensor
+  for (uint32_t s = 0; s < h->B; s++)
+    cudaMemcpy2DAsync(d_in + (size_t)s * h->M * L, sizeof(float) * L, in_host + s * ss, sizeof(float) * ms, sizeof(float) * L, h->M,
+                      cudaMemcpyHostToDevice, st);
+  int rc = bf_process_batch_device(h, d_in, (size_t)h->M * L, L, d_out, L, n_hops, ev, n_ev, st);
+  if (rc == BF_OK) {
+    cudaMemcpy2DAsync(out_host, sizeof(float) * os, d_out, sizeof(float) * L, sizeof(float) * L, h->B, cudaMemcpyDeviceToHost, st);
+    cudaError_t e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) rc = fail(BF_ERR_CUDA, cudaGetErrorString(e));
+  }
+  cudaFree(d_in); cudaFree(d_out);
+  return rc;
+}
+
+extern "C" int bf_process_hop(bf_handle* h, const float* const* in, float* out, uint32_t nframes) {
+  if (!h || !in || !out) return fail(BF_ERR_INVALID, "bf_process_hop: null argument");
+  if (h->B != 1) return fail(BF_ERR_INVALID, "bf_process_hop: handle must have n_streams == 1");
+  if (nframes != h->H) return fail(BF_ERR_INVALID, "bf_process_hop: nframes != hop (JACK period changed?)");
+  CUDA_TRY(cudaSetDevice(h->dev));
+  cudaStream_t st = h->own_stream;
+  for (uint32_t m = 0; m < h->M; m++) memcpy(h->h_stage_in + (size_t)m * h->H, in[m], sizeof(float) * h->H);
+  CUDA_TRY(cudaMemcpyAsync(h->d_stage_in, h->h_stage_in, sizeof(float) * h->M * h->H, cudaMemcpyHostToDevice, st));
+  int rc = bf_process_batch_device(h, h->d_stage_in, (size_t)h->M * h->H, h->H, h->d_stage_out, h->H, 1, nullptr, 0, st);
+  if (rc != BF_OK) return rc;
+  CUDA_TRY(cudaMemcpyAsync(h->h_stage_out, h->d_stage_out, sizeof(float) * h->H, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  memcpy(out, h->h_stage_out, sizeof(float) * h->H);
+  return BF_OK;
+}
+
+extern "C" int bf_set_capture(bf_handle* h, uint8_t* dev_flags) {
+  if (!h) return fail(BF_ERR_INVALID, "null handle");
+  h->d_capture = dev_flags;
+  return BF_OK;
+}
+
+extern "C" int bf_srp_batch_device(bf_handle*, const float*, size_t, size_t, const float*, uint32_t, float*, uint32_t, void*) {
+  return fail(BF_ERR_INVALID, "bf_srp_batch_device: not built yet");
+}
+
+extern "C" uint32_t bf_fft_win(const bf_handle* h) { return h ? h->N : 0; }
+extern "C" uint64_t bf_kernel_launches(const bf_handle* h) { return h ? h->launches : 0; }
+extern "C" const char* bf_last_error(void) { return g_err.c_str(); }
+extern "C" const char* bf_version(void) { return "beamform_b200 0.1 (sm_100a)"; }
