@@ -3,6 +3,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#define BF_MAX_MICS_DEV 64
+
 namespace bf {
 
 enum { ALGO_DAS = 0, ALGO_MVDR = 1, ALGO_LCMV = 2, ALGO_GSS = 3, ALGO_PHASE = 4, ALGO_PHASEMPF = 5 };
@@ -39,6 +41,7 @@ struct KernelParams {
   int P;                    // past_windows
   float2* hist;             // [B][Lsel][P][M]  mvdr/lcmv history ring, slot = frame % P
   const int* sel_slot;      // [L] -> slot in the in-band compact list or -1
+  const int* sel_list;      // [Lsel] -> logical bin
   int Lsel;
   float mu, lambda_mu;      // gss: mu, (1 - lambda*mu)
   float2* gss_w;            // [B][Lsel][C][M]

@@ -24,6 +24,7 @@
 namespace bf {
 cudaError_t launch_frames_kernel_1024(int algo, const KernelParams& p, cudaStream_t st);
 cudaError_t launch_save_prev_hop(const KernelParams& p, int last_hop, cudaStream_t st);
+cudaError_t launch_gss_reset(const KernelParams& p, cudaStream_t st);
 size_t frames_kernel_smem(int M);
 }   // namespace bf
 
@@ -73,6 +74,14 @@ struct bf_handle {
   uint8_t* d_inband = nullptr;
   uint8_t* d_capture = nullptr;
   size_t steer_cap = 0;
+  int* d_sel_slot = nullptr;
+  int* d_sel_list = nullptr;
+  int Lsel = 0;
+  float2* d_hist = nullptr;     // mvdr/lcmv: [B][Lsel][P][M]
+  float2* d_gss_w = nullptr;    // gss: [B][Lsel][C][M]
+  double* d_win_d = nullptr;
+  double2* d_twid_d = nullptr;
+  bool gss_reset_pending = true;
   // hop-at-a-time staging
   float* h_stage_in = nullptr;
   float* h_stage_out = nullptr;
@@ -257,6 +266,7 @@ static void update_weights(bf_handle* h, bool ini) {
     }
   }
   h->tables_dirty = true;
+  h->gss_reset_pending = true;   // gss.cpp:90-93
 }
 
 static uint32_t bin_of_logical(const bf_handle* h, uint32_t l) { return l; }   // l = N/2+1 is FFT bin N/2+1 itself
@@ -353,6 +363,41 @@ extern "C" int bf_create(bf_handle** out, const bf_config* cfg, uint32_t n_strea
             cudaMallocHost(&h->h_stage_in, sizeof(float) * h->M * h->H) == cudaSuccess &&
             cudaMallocHost(&h->h_stage_out, sizeof(float) * h->H) == cudaSuccess;
   if (!ok) { bf_destroy(h); return fail(BF_ERR_ALLOC, "bf_create: device allocation failed"); }
+  {
+    // in-band logical bins (fixed by freq_min/freq_max at create) -> compact state slots
+    std::vector<int> slot(h->L, -1), list;
+    for (uint32_t l = 0; l < h->L; l++) {
+      double f = std::fabs(h->freqs[l]);
+      if (f >= cfg->freq_min && f <= cfg->freq_max) { slot[l] = (int)list.size(); list.push_back((int)l); }
+    }
+    h->Lsel = (int)list.size();
+    const bool sel_algo = cfg->algo == BF_ALGO_MVDR || cfg->algo == BF_ALGO_LCMV || cfg->algo == BF_ALGO_GSS;
+    if (sel_algo) {
+      if ((cfg->algo != BF_ALGO_GSS) && h->M > 8) { bf_destroy(h); return fail(BF_ERR_INVALID, "bf_create: mvdr/lcmv support at most 8 microphones in this build"); }
+      if (cfg->past_windows < 1) { bf_destroy(h); return fail(BF_ERR_INVALID, "bf_create: past_windows must be >= 1"); }
+      std::vector<double> win(h->N);
+      std::vector<double2> twd(h->N);
+      for (uint32_t n = 0; n < h->N; n++) {
+        win[n] = std::sqrt(0.5 - 0.5 * std::cos(2 * kPi * n / (h->N)));   // util.h:201-211
+        double ang = -2.0 * kPi * (double)n / (double)h->N;
+        twd[n] = make_double2(std::cos(ang), std::sin(ang));
+      }
+      const size_t nl = std::max(1, h->Lsel);
+      bool ok2 = cudaMalloc(&h->d_sel_slot, sizeof(int) * h->L) == cudaSuccess && cudaMalloc(&h->d_sel_list, sizeof(int) * nl) == cudaSuccess &&
+                 cudaMalloc(&h->d_win_d, sizeof(double) * h->N) == cudaSuccess && cudaMalloc(&h->d_twid_d, sizeof(double2) * h->N) == cudaSuccess;
+      if (ok2 && cfg->algo != BF_ALGO_GSS) {
+        const size_t nh = (size_t)h->B * nl * cfg->past_windows * h->M;
+        ok2 = cudaMalloc(&h->d_hist, sizeof(float2) * nh) == cudaSuccess;
+        if (ok2) cudaMemset(h->d_hist, 0, sizeof(float2) * nh);   // past_ffts.setZero() (mvdr.cpp:229-233)
+      }
+      if (ok2 && cfg->algo == BF_ALGO_GSS) ok2 = cudaMalloc(&h->d_gss_w, sizeof(float2) * (size_t)h->B * nl * 8 * h->M) == cudaSuccess;
+      if (!ok2) { bf_destroy(h); return fail(BF_ERR_ALLOC, "bf_create: device allocation failed (state)"); }
+      cudaMemcpy(h->d_sel_slot, slot.data(), sizeof(int) * h->L, cudaMemcpyHostToDevice);
+      if (h->Lsel) cudaMemcpy(h->d_sel_list, list.data(), sizeof(int) * h->Lsel, cudaMemcpyHostToDevice);
+      cudaMemcpy(h->d_win_d, win.data(), sizeof(double) * h->N, cudaMemcpyHostToDevice);
+      cudaMemcpy(h->d_twid_d, twd.data(), sizeof(double2) * h->N, cudaMemcpyHostToDevice);
+    }
+  }
   cudaMemset(h->d_prev_hop, 0, sizeof(float) * prev_n);   // util.h:275-277: one hop of zeros pre-loaded
   cudaMemset(h->d_tail, 0, sizeof(float) * tail_n);       // util.h:285: calloc'ed out_buff
   int rc = upload_tables(h, h->own_stream);
@@ -367,6 +412,7 @@ extern "C" void bf_destroy(bf_handle* h) {
   if (h->own_stream) { cudaStreamSynchronize(h->own_stream); cudaStreamDestroy(h->own_stream); }
   cudaFree(h->d_prev_hop); cudaFree(h->d_tail); cudaFree(h->d_steer); cudaFree(h->d_das_ceff); cudaFree(h->d_inband);
   cudaFree(h->d_stage_in); cudaFree(h->d_stage_out);
+  cudaFree(h->d_sel_slot); cudaFree(h->d_sel_list); cudaFree(h->d_hist); cudaFree(h->d_gss_w); cudaFree(h->d_win_d); cudaFree(h->d_twid_d);
   if (h->h_stage_in) cudaFreeHost(h->h_stage_in);
   if (h->h_stage_out) cudaFreeHost(h->h_stage_out);
   delete h;
@@ -480,6 +526,22 @@ static int run_segment(bf_handle* h, const float* in, size_t ss, size_t ms, floa
   if (h->d_capture) {
     p.capture = h->d_capture + (size_t)h0 * h->N;
     p.capture_stream_stride = (long long)call_hops * h->N;
+  }
+  if (h->C > 8 && (h->cfg.algo == BF_ALGO_LCMV || h->cfg.algo == BF_ALGO_GSS))
+    return fail(BF_ERR_INVALID, "more than 7 interferers are not supported by this build");
+  p.thr_mag = (float)(h->cfg.freq_mag_threshold * (double)h->M * (double)h->N);
+  p.thr_mag_d = h->cfg.freq_mag_threshold;
+  p.P = (int)h->cfg.past_windows;
+  p.hist = h->d_hist; p.sel_slot = h->d_sel_slot; p.sel_list = h->d_sel_list; p.Lsel = h->Lsel;
+  p.mu = (float)h->cfg.mu;
+  p.lambda_mu = (float)(1 - h->cfg.lambda * h->cfg.mu);
+  p.gss_w = h->d_gss_w;
+  p.gss_dj2_scale = (float)(2 * (1 / (size_t)h->C));   // gss.cpp:133: integer arithmetic (SURVEY B-7)
+  p.win_d = h->d_win_d; p.twid_d = h->d_twid_d;
+  if (h->cfg.algo == BF_ALGO_GSS && h->gss_reset_pending) {
+    CUDA_TRY(bf::launch_gss_reset(p, st));
+    h->launches++;
+    h->gss_reset_pending = false;
   }
   CUDA_TRY(bf::launch_frames_kernel_1024(h->cfg.algo, p, st));
   CUDA_TRY(bf::launch_save_prev_hop(p, (int)(h1 - h0) - 1, st));

@@ -13,6 +13,7 @@
 // window, OLA), das.cpp:47-70 and the apply_weights of every other node (see each phase_b_* below).
 #include "bf_device.h"
 #include "warp_fft1024.cuh"
+#include "phase_b_select.cuh"
 
 namespace bf {
 
@@ -32,8 +33,9 @@ __device__ __forceinline__ const float* hop_ptr(const KernelParams& p, int s, in
 // FORWARD for one microphone: z[n] = 0.5*w[n]*(frame_t[n] + i*frame_{t+1}[n]), Z = FFT_1024(z) -> zbuf (linear [1024]).
 // frame_t = [hop t-1 | hop t] (util.h:217-242: ring buffer holds previous + new hop).  The 0.5 makes the
 // later even/odd separation X_t = Z[j] + conj(Z[N-j]) exact without a scale.
+template <bool ENERGY>
 __device__ __forceinline__ void forward_mic(const KernelParams& p, int s, int ch, PairCtx pc, float2* zbuf, const float2* tw,
-                                            int lane, float s_l, float c_l) {
+                                            int lane, float s_l, float c_l, float* sqrtE0, float* sqrtE1) {
   const float* ha = hop_ptr(p, s, ch, pc.t - 1);
   const float* hb = hop_ptr(p, s, ch, pc.t);
   const float* hc = pc.two ? hop_ptr(p, s, ch, pc.t + 1) : hb;
@@ -51,6 +53,14 @@ __device__ __forceinline__ void forward_mic(const KernelParams& p, int s, int ch
     v[brev5(r)] = make_float2(a[r] * w0, b[r] * w0);
     v[brev5(r + 16)] = make_float2(b[r] * w1, c[r] * w1);
   });
+  if (ENERGY) {   // sqrt of the windowed frame energies: scale of the FP32 FFT's absolute error (gate guard band)
+    float e0 = 0.f, e1 = 0.f;
+#pragma unroll
+    for (int r = 0; r < 32; r++) { e0 = fmaf(v[r].x, v[r].x, e0); e1 = fmaf(v[r].y, v[r].y, e1); }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { e0 += __shfl_xor_sync(0xffffffffu, e0, o); e1 += __shfl_xor_sync(0xffffffffu, e1, o); }
+    if (lane == 0) { sqrtE0[ch] = 2.0f * sqrtf(e0); sqrtE1[ch] = 2.0f * sqrtf(e1); }
+  }
   warp_fft1024<-1>(v, zbuf, tw, lane);
 #pragma unroll
   for (int k2 = 0; k2 < 32; k2++) zbuf[k2 * 32 + lane] = v[k2];
@@ -107,6 +117,8 @@ __global__ void __launch_bounds__(288) frames_kernel_1024(const KernelParams p) 
   float2* tw = reinterpret_cast<float2*>(smem_raw);       // [32][32] W_1024^{lane*k1}
   float2* gbuf = tw + 1024;                                // G, then warp 0's exchange tile
   float2* zall = gbuf + kXTile;                            // [M] tiles: exchange tile, then Z linear
+  SelScratch& sel = *reinterpret_cast<SelScratch*>(zall + (size_t)p.M * kXTile);
+  constexpr bool kSel = (ALGO == ALGO_MVDR || ALGO == ALGO_LCMV || ALGO == ALGO_GSS);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
   const int s = blockIdx.x;
 
@@ -140,11 +152,13 @@ __global__ void __launch_bounds__(288) frames_kernel_1024(const KernelParams p) 
         inverse_pair(p, s, pv, gbuf, gbuf, tw, lane, s_o, c_o, tail);
       }
     } else if (ip < npairs) {
-      for (int ch = warp - 1; ch < p.M; ch += nwarps - 1) forward_mic(p, s, ch, pc, zall + ch * kXTile, tw, lane, s_l, c_l);
+      for (int ch = warp - 1; ch < p.M; ch += nwarps - 1)
+        forward_mic<kSel>(p, s, ch, pc, zall + ch * kXTile, tw, lane, s_l, c_l, sel.sqrtE[0], sel.sqrtE[1]);
     }
     if (ip == npairs) break;
     __syncthreads();   // Z complete; previous G consumed
     if (ALGO == ALGO_DAS) phase_b_das(p, zall, gbuf, tid, blockDim.x);
+    if (kSel) phase_b_select<ALGO>(p, s, pc.t, pc.two, zall, gbuf, sel, tid, blockDim.x);
     __syncthreads();   // G complete; Z consumed
   }
   if (warp == 0) {
@@ -161,7 +175,24 @@ __global__ void save_prev_hop_kernel(const KernelParams p, int last_hop) {
   for (int i = threadIdx.x; i < p.H; i += blockDim.x) dst[i] = src[i];
 }
 
-size_t frames_kernel_smem(int M) { return sizeof(float2) * (1024 + (size_t)kXTile * (1 + M)); }
+// gss.cpp:90-93: every update_weights resets sep_matrix[j] = weights[j]^H (adaptation is discarded)
+__global__ void gss_reset_kernel(const KernelParams p) {
+  const size_t per = (size_t)p.Lsel * p.C * p.M;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < (size_t)p.n_streams * per; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t r = i % per;
+    const int slot = (int)(r / ((size_t)p.C * p.M));
+    const int c = (int)((r / p.M) % p.C), m = (int)(r % p.M);
+    const int l = p.sel_list[slot];
+    const float2 a = p.steer[((size_t)l * p.C + c) * p.M + m];
+    p.gss_w[i] = make_float2(a.x, -a.y);
+  }
+}
+cudaError_t launch_gss_reset(const KernelParams& p, cudaStream_t st) {
+  gss_reset_kernel<<<296, 256, 0, st>>>(p);
+  return cudaGetLastError();
+}
+
+size_t frames_kernel_smem(int M) { return sizeof(float2) * (1024 + (size_t)kXTile * (1 + M)) + sizeof(SelScratch); }
 
 cudaError_t launch_frames_kernel_1024(int algo, const KernelParams& p, cudaStream_t st) {
   const int fwd = p.M < 8 ? p.M : 8;
@@ -170,6 +201,9 @@ cudaError_t launch_frames_kernel_1024(int algo, const KernelParams& p, cudaStrea
   void (*k)(KernelParams) = nullptr;
   switch (algo) {
     case ALGO_DAS: k = frames_kernel_1024<ALGO_DAS>; break;
+    case ALGO_MVDR: k = frames_kernel_1024<ALGO_MVDR>; break;
+    case ALGO_LCMV: k = frames_kernel_1024<ALGO_LCMV>; break;
+    case ALGO_GSS: k = frames_kernel_1024<ALGO_GSS>; break;
     default: return cudaErrorNotSupported;
   }
   cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

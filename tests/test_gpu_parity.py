@@ -63,3 +63,86 @@ def test_das_hop_at_a_time_callback_matches_batch():
     b = bf.Beamformer(cfg, n_streams=1)
     got = np.concatenate([b.process_hop(x[:, t * H:(t + 1) * H]) for t in range(12)])
     assert rel_l2(got, ref) <= REL_L2_TOL
+
+
+# ---------------------------------------------------------------------------------------------
+# magnitude-gated nodes: mvdr / lcmv / gss (device-resident path, selection flags captured)
+# ---------------------------------------------------------------------------------------------
+def run_device(cfg, x, events=(), capture=True):
+    import torch
+    B, M, L = x.shape
+    T = L // H
+    b = bf.Beamformer(cfg, n_streams=B)
+    xin = torch.from_numpy(x).cuda()
+    out = torch.empty((B, L), dtype=torch.float32, device="cuda")
+    flags = torch.zeros((B, T, 2 * H), dtype=torch.uint8, device="cuda") if capture else None
+    if capture:
+        b.set_capture(flags.data_ptr())
+    b.process_device(xin.data_ptr(), out.data_ptr(), T, stream_ptr=torch.cuda.current_stream().cuda_stream, events=events)
+    torch.cuda.synchronize()
+    return out.cpu().numpy(), (flags.cpu().numpy() if capture else None), b
+
+
+def oracle_with_flags(cfg, x, events=()):
+    outs, sels, msks = [], [], []
+    for bidx in range(x.shape[0]):
+        o, s, m = Oracle(cfg).process(x[bidx], events=events, want_flags=True)
+        outs.append(o), sels.append(s), msks.append(m)
+    return np.stack(outs), np.stack(sels), np.stack(msks)
+
+
+def finite_rel_l2(got, ref):
+    ok = np.isfinite(ref)
+    assert np.array_equal(np.isfinite(got), ok), "non-finite samples must coincide (cold-start NaNs, SURVEY B-10)"
+    return rel_l2(got[ok], ref[ok])
+
+
+@pytest.mark.parametrize("mics,theta", [("circ8", 0.0), ("aira3", 20.0)])
+def test_mvdr_matches_oracle_and_selection_is_bit_exact(mics, theta):
+    cfg = bf.make_config("mvdr", mics=mics, initial_angle=theta)
+    x = synth_batch(bf.GEOMETRIES[mics], 3, 61 * H, seed=21)
+    ref, sel, _ = oracle_with_flags(cfg, x)
+    got, flags, _ = run_device(cfg, x)
+    assert sel.sum() > 1000, "the test signal must exercise the gate"
+    assert np.array_equal(flags & 1, sel), "selected-bin set must be bit-exact"
+    err = finite_rel_l2(got, ref)
+    print("mvdr", mics, "rel_l2", err, "selected fraction", sel.mean())
+    assert err <= REL_L2_TOL
+
+
+def test_lcmv_with_interference_events_matches_oracle():
+    cfg = bf.make_config("lcmv", mics="circ8", initial_angle=0.0, interferers=(80.0, -60.0, 150.0))
+    x = synth_batch(bf.GEOMETRIES["circ8"], 2, 100 * H, seed=31)
+    # SURVEY.md §8d event script, compressed in time: theta move, interferer move, add, too-close => remove, invalid id
+    events = [(20, "theta", 20.0), (40, "interf", 2, -55.0), (60, "interf", 4, 120.0), (80, "interf", 1, 119.5), (90, "interf", 0, 10.0)]
+    ref, sel, _ = oracle_with_flags(cfg, x, events=events)
+    got, flags, b = run_device(cfg, x, events=events)
+    o = Oracle(cfg)
+    o.process(x[0], events=events)
+    assert b.interferences == o.interferences, "interference list must be bit-exact"
+    assert np.array_equal(flags & 1, sel)
+    err = finite_rel_l2(got, ref)
+    print("lcmv rel_l2", err)
+    assert err <= REL_L2_TOL
+
+
+def test_gss_with_events_matches_oracle():
+    cfg = bf.make_config("gss", mics="circ8", initial_angle=0.0, interferers=(80.0, -60.0, 150.0))
+    x = synth_batch(bf.GEOMETRIES["circ8"], 2, 100 * H, seed=41)
+    events = [(20, "theta", 20.0), (40, "interf", 2, -55.0), (60, "interf", 4, 120.0), (80, "interf", 1, 119.5), (90, "interf", 0, 10.0)]
+    ref, sel, _ = oracle_with_flags(cfg, x, events=events)
+    got, flags, b = run_device(cfg, x, events=events)
+    assert np.array_equal(flags & 1, sel)
+    err = finite_rel_l2(got, ref)
+    print("gss rel_l2", err)
+    assert err <= REL_L2_TOL
+
+
+def test_gss_without_interferers_keeps_geometric_gradient():
+    # K = 0: the integer 1/(K+1) is 1, so dJ2 is active (SURVEY B-7)
+    cfg = bf.make_config("gss", mics="aira3", initial_angle=10.0)
+    x = synth_batch(bf.GEOMETRIES["aira3"], 2, 50 * H, seed=43)
+    ref, sel, _ = oracle_with_flags(cfg, x)
+    got, flags, _ = run_device(cfg, x)
+    assert np.array_equal(flags & 1, sel)
+    assert finite_rel_l2(got, ref) <= REL_L2_TOL
