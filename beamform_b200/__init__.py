@@ -94,6 +94,8 @@ def lib():
     L.bf_set_capture.argtypes = [C.c_void_p, C.c_void_p]
     L.bf_srp_batch_device.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, P(C.c_float), C.c_uint32, C.c_void_p,
                                       C.c_uint32, C.c_void_p]
+    L.bf_set_profiling.argtypes = [C.c_void_p, C.c_int]
+    L.bf_get_profile.argtypes = [C.c_void_p, P(C.c_double), P(C.c_uint64)]
     L.bf_fft_win.argtypes = [C.c_void_p]
     L.bf_fft_win.restype = C.c_uint32
     L.bf_kernel_launches.argtypes = [C.c_void_p]
@@ -233,6 +235,15 @@ class Beamformer:
 
     def set_capture(self, dev_ptr):
         _check(lib().bf_set_capture(self._h, dev_ptr), "bf_set_capture")
+
+    def set_profiling(self, on=True):
+        _check(lib().bf_set_profiling(self._h, 1 if on else 0), "bf_set_profiling")
+
+    def get_profile(self):
+        """(summed device ms of the fused frames kernel, launches) since the last call."""
+        ms, n = C.c_double(), C.c_uint64()
+        _check(lib().bf_get_profile(self._h, C.byref(ms), C.byref(n)), "bf_get_profile")
+        return ms.value, int(n.value)
 
     @property
     def kernel_launches(self):

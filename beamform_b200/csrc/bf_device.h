@@ -21,6 +21,7 @@ struct KernelParams {
   float* out;
   long long out_stream_stride;
   int n_streams, M, H, N;
+  int stream_begin;         // first stream of this launch (grid = n_streams CTAs, stream = blockIdx.x + stream_begin)
   int hop_begin, hop_end;   // this launch processes hops [hop_begin, hop_end) of the arrays above
   int frame_index0;         // global frame counter of hop 0 of this call (history / MCRA bookkeeping)
   // ---- per-stream state carried between launches / calls ----

@@ -82,6 +82,12 @@ struct bf_handle {
   double* d_win_d = nullptr;
   double2* d_twid_d = nullptr;
   bool gss_reset_pending = true;
+  // host-batch staging + copy/compute overlap
+  float* d_io_in = nullptr;
+  float* d_io_out = nullptr;
+  size_t io_in_cap = 0, io_out_cap = 0;
+  cudaStream_t st_h2d = nullptr, st_d2h = nullptr;
+  cudaEvent_t ev_in[8] = {nullptr}, ev_k[8] = {nullptr};
   // hop-at-a-time staging
   float* h_stage_in = nullptr;
   float* h_stage_out = nullptr;
@@ -92,6 +98,8 @@ struct bf_handle {
   uint64_t launches = 0;
   int drop_left = 0;
   bool tables_dirty = true;
+  bool profiling = false;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t> > prof_events;
   std::mutex mtx;
   std::vector<PendingEvent> pending;
 };
@@ -353,6 +361,12 @@ extern "C" int bf_create(bf_handle** out, const bf_config* cfg, uint32_t n_strea
 
   cudaError_t e = cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking);
   if (e != cudaSuccess) { delete h; return fail(BF_ERR_CUDA, cudaGetErrorString(e)); }
+  cudaStreamCreateWithFlags(&h->st_h2d, cudaStreamNonBlocking);
+  cudaStreamCreateWithFlags(&h->st_d2h, cudaStreamNonBlocking);
+  for (int i = 0; i < 8; i++) {
+    cudaEventCreateWithFlags(&h->ev_in[i], cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&h->ev_k[i], cudaEventDisableTiming);
+  }
   const size_t prev_n = (size_t)h->B * h->M * h->H, tail_n = (size_t)h->B * h->H;
   bool ok = cudaMalloc(&h->d_prev_hop, sizeof(float) * prev_n) == cudaSuccess &&
             cudaMalloc(&h->d_tail, sizeof(float) * tail_n) == cudaSuccess &&
@@ -411,7 +425,10 @@ extern "C" void bf_destroy(bf_handle* h) {
   cudaSetDevice(h->dev);
   if (h->own_stream) { cudaStreamSynchronize(h->own_stream); cudaStreamDestroy(h->own_stream); }
   cudaFree(h->d_prev_hop); cudaFree(h->d_tail); cudaFree(h->d_steer); cudaFree(h->d_das_ceff); cudaFree(h->d_inband);
-  cudaFree(h->d_stage_in); cudaFree(h->d_stage_out);
+  cudaFree(h->d_stage_in); cudaFree(h->d_stage_out); cudaFree(h->d_io_in); cudaFree(h->d_io_out);
+  if (h->st_h2d) cudaStreamDestroy(h->st_h2d);
+  if (h->st_d2h) cudaStreamDestroy(h->st_d2h);
+  for (int i = 0; i < 8; i++) { if (h->ev_in[i]) cudaEventDestroy(h->ev_in[i]); if (h->ev_k[i]) cudaEventDestroy(h->ev_k[i]); }
   cudaFree(h->d_sel_slot); cudaFree(h->d_sel_list); cudaFree(h->d_hist); cudaFree(h->d_gss_w); cudaFree(h->d_win_d); cudaFree(h->d_twid_d);
   if (h->h_stage_in) cudaFreeHost(h->h_stage_in);
   if (h->h_stage_out) cudaFreeHost(h->h_stage_out);
@@ -506,7 +523,7 @@ __global__ void zero_hops_kernel(float* out, long long stride, int n) {
 }
 
 static int run_segment(bf_handle* h, const float* in, size_t ss, size_t ms, float* out, size_t os, uint32_t h0, uint32_t h1,
-                       uint32_t call_hops, cudaStream_t st) {
+                       uint32_t call_hops, cudaStream_t st, uint32_t s0 = 0, uint32_t ns = 0) {
   if (h1 <= h0) return BF_OK;
   int rc = upload_tables(h, st);
   if (rc != BF_OK) return rc;
@@ -516,7 +533,7 @@ static int run_segment(bf_handle* h, const float* in, size_t ss, size_t ms, floa
   p.in_stream_stride = (long long)ss; p.in_mic_stride = (long long)ms;
   p.out = out + (size_t)h0 * h->H;
   p.out_stream_stride = (long long)os;
-  p.n_streams = h->B; p.M = h->M; p.H = h->H; p.N = h->N;
+  p.n_streams = ns ? ns : h->B; p.stream_begin = (int)s0; p.M = h->M; p.H = h->H; p.N = h->N;
   p.hop_begin = 0; p.hop_end = (int)(h1 - h0);
   p.frame_index0 = (int)(h->frames_done & 0x7fffffff);
   p.prev_hop = h->d_prev_hop; p.tail = h->d_tail;
@@ -539,14 +556,26 @@ static int run_segment(bf_handle* h, const float* in, size_t ss, size_t ms, floa
   p.gss_dj2_scale = (float)(2 * (1 / (size_t)h->C));   // gss.cpp:133: integer arithmetic (SURVEY B-7)
   p.win_d = h->d_win_d; p.twid_d = h->d_twid_d;
   if (h->cfg.algo == BF_ALGO_GSS && h->gss_reset_pending) {
-    CUDA_TRY(bf::launch_gss_reset(p, st));
+    bf::KernelParams pr = p;
+    pr.n_streams = h->B; pr.stream_begin = 0;
+    CUDA_TRY(bf::launch_gss_reset(pr, st));
     h->launches++;
     h->gss_reset_pending = false;
   }
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  if (h->profiling) {
+    CUDA_TRY(cudaEventCreate(&ev0));
+    CUDA_TRY(cudaEventCreate(&ev1));
+    CUDA_TRY(cudaEventRecord(ev0, st));
+  }
   CUDA_TRY(bf::launch_frames_kernel_1024(h->cfg.algo, p, st));
+  if (h->profiling) {
+    CUDA_TRY(cudaEventRecord(ev1, st));
+    h->prof_events.push_back(std::make_pair(ev0, ev1));
+  }
   CUDA_TRY(bf::launch_save_prev_hop(p, (int)(h1 - h0) - 1, st));
   h->launches += 2;
-  h->frames_done += h1 - h0;
+  if (s0 + p.n_streams >= h->B) h->frames_done += h1 - h0;   // the last stream chunk closes the segment
   return BF_OK;
 }
 
@@ -578,27 +607,70 @@ extern "C" int bf_process_batch_device(bf_handle* h, const float* in, size_t ss,
   return BF_OK;
 }
 
+static int ensure_io_staging(bf_handle* h, size_t in_floats, size_t out_floats) {
+  if (in_floats > h->io_in_cap) {
+    if (h->d_io_in) cudaFree(h->d_io_in);
+    h->d_io_in = nullptr; h->io_in_cap = 0;
+    if (cudaMalloc(&h->d_io_in, sizeof(float) * in_floats) != cudaSuccess) return fail(BF_ERR_ALLOC, "bf_process_batch: input staging alloc");
+    h->io_in_cap = in_floats;
+  }
+  if (out_floats > h->io_out_cap) {
+    if (h->d_io_out) cudaFree(h->d_io_out);
+    h->d_io_out = nullptr; h->io_out_cap = 0;
+    if (cudaMalloc(&h->d_io_out, sizeof(float) * out_floats) != cudaSuccess) return fail(BF_ERR_ALLOC, "bf_process_batch: output staging alloc");
+    h->io_out_cap = out_floats;
+  }
+  return BF_OK;
+}
+
+// Host-buffer entry (what a rosjack-side caller or the offline driver uses): H2D, kernels, D2H.
+// Without scheduled events the batch is cut into stream chunks that flow through three CUDA streams
+// (copy-in / compute / copy-out) so PCIe transfers overlap the kernels.
 extern "C" int bf_process_batch(bf_handle* h, const float* in_host, size_t ss, size_t ms, float* out_host, size_t os,
                                 uint32_t n_hops, const bf_event* ev, uint32_t n_ev) {
   if (!h || !in_host || !out_host) return fail(BF_ERR_INVALID, "bf_process_batch: null argument");
   CUDA_TRY(cudaSetDevice(h->dev));
   const size_t L = (size_t)n_hops * h->H;
-  float *d_in = nullptr, *d_out = nullptr;
-  CUDA_TRY(cudaMalloc(&d_in, sizeof(float) * h->B * h->M * L));
-  if (cudaMalloc(&d_out, sizeof(float) * h->B * L) != cudaSuccess) { cudaFree(d_in); return fail(BF_ERR_ALLOC, "bf_process_batch: alloc"); }
-  cudaStream_t st = h->own_stream;
-  // gather each (stream, mic) row into a dense [B][M][L] device tensor
-  for (uint32_t s = 0; s < h->B; s++)
-    cudaMemcpy2DAsync(d_in + (size_t)s * h->M * L, sizeof(float) * L, in_host + s * ss, sizeof(float) * ms, sizeof(float) * L, h->M,
-                      cudaMemcpyHostToDevice, st);
-  int rc = bf_process_batch_device(h, d_in, (size_t)h->M * L, L, d_out, L, n_hops, ev, n_ev, st);
-  if (rc == BF_OK) {
-    cudaMemcpy2DAsync(out_host, sizeof(float) * os, d_out, sizeof(float) * L, sizeof(float) * L, h->B, cudaMemcpyDeviceToHost, st);
-    cudaError_t e = cudaStreamSynchronize(st);
-    if (e != cudaSuccess) rc = fail(BF_ERR_CUDA, cudaGetErrorString(e));
+  int rc = ensure_io_staging(h, (size_t)h->B * h->M * L, (size_t)h->B * L);
+  if (rc != BF_OK) return rc;
+  float *d_in = h->d_io_in, *d_out = h->d_io_out;
+  drain_pending(h);
+  const bool dense = (ms == L && ss == (size_t)h->M * L);
+  if (n_ev == 0 && h->drop_left == 0 && h->B >= 16) {
+    rc = upload_tables(h, h->own_stream);
+    if (rc != BF_OK) return rc;
+    const uint32_t nchunk = 8, per = (h->B + nchunk - 1) / nchunk;
+    for (uint32_t c = 0, s0 = 0; s0 < h->B; c++, s0 += per) {
+      const uint32_t ns = std::min(per, h->B - s0);
+      if (dense) {
+        CUDA_TRY(cudaMemcpyAsync(d_in + (size_t)s0 * h->M * L, in_host + (size_t)s0 * ss, sizeof(float) * ns * h->M * L, cudaMemcpyHostToDevice, h->st_h2d));
+      } else {
+        for (uint32_t s = s0; s < s0 + ns; s++)
+          CUDA_TRY(cudaMemcpy2DAsync(d_in + (size_t)s * h->M * L, sizeof(float) * L, in_host + s * ss, sizeof(float) * ms, sizeof(float) * L, h->M,
+                                     cudaMemcpyHostToDevice, h->st_h2d));
+      }
+      CUDA_TRY(cudaEventRecord(h->ev_in[c], h->st_h2d));
+      CUDA_TRY(cudaStreamWaitEvent(h->own_stream, h->ev_in[c], 0));
+      rc = run_segment(h, d_in, (size_t)h->M * L, L, d_out, L, 0, n_hops, n_hops, h->own_stream, s0, ns);
+      if (rc != BF_OK) return rc;
+      CUDA_TRY(cudaEventRecord(h->ev_k[c], h->own_stream));
+      CUDA_TRY(cudaStreamWaitEvent(h->st_d2h, h->ev_k[c], 0));
+      CUDA_TRY(cudaMemcpy2DAsync(out_host + (size_t)s0 * os, sizeof(float) * os, d_out + (size_t)s0 * L, sizeof(float) * L, sizeof(float) * L, ns,
+                                 cudaMemcpyDeviceToHost, h->st_d2h));
+    }
+    CUDA_TRY(cudaStreamSynchronize(h->st_d2h));
+    CUDA_TRY(cudaStreamSynchronize(h->own_stream));
+    return BF_OK;
   }
-  cudaFree(d_in); cudaFree(d_out);
-  return rc;
+  cudaStream_t st = h->own_stream;
+  for (uint32_t s = 0; s < h->B; s++)
+    CUDA_TRY(cudaMemcpy2DAsync(d_in + (size_t)s * h->M * L, sizeof(float) * L, in_host + s * ss, sizeof(float) * ms, sizeof(float) * L, h->M,
+                               cudaMemcpyHostToDevice, st));
+  rc = bf_process_batch_device(h, d_in, (size_t)h->M * L, L, d_out, L, n_hops, ev, n_ev, st);
+  if (rc != BF_OK) return rc;
+  CUDA_TRY(cudaMemcpy2DAsync(out_host, sizeof(float) * os, d_out, sizeof(float) * L, sizeof(float) * L, h->B, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  return BF_OK;
 }
 
 extern "C" int bf_process_hop(bf_handle* h, const float* const* in, float* out, uint32_t nframes) {
@@ -625,6 +697,28 @@ extern "C" int bf_set_capture(bf_handle* h, uint8_t* dev_flags) {
 
 extern "C" int bf_srp_batch_device(bf_handle*, const float*, size_t, size_t, const float*, uint32_t, float*, uint32_t, void*) {
   return fail(BF_ERR_INVALID, "bf_srp_batch_device: not built yet");
+}
+
+extern "C" int bf_set_profiling(bf_handle* h, int enabled) {
+  if (!h) return fail(BF_ERR_INVALID, "null handle");
+  h->profiling = enabled != 0;
+  return BF_OK;
+}
+extern "C" int bf_get_profile(bf_handle* h, double* kernel_ms, uint64_t* n) {
+  if (!h || !kernel_ms || !n) return fail(BF_ERR_INVALID, "null argument");
+  double tot = 0;
+  for (auto& e : h->prof_events) {
+    CUDA_TRY(cudaEventSynchronize(e.second));
+    float ms = 0;
+    CUDA_TRY(cudaEventElapsedTime(&ms, e.first, e.second));
+    tot += ms;
+    cudaEventDestroy(e.first);
+    cudaEventDestroy(e.second);
+  }
+  *kernel_ms = tot;
+  *n = h->prof_events.size();
+  h->prof_events.clear();
+  return BF_OK;
 }
 
 extern "C" uint32_t bf_fft_win(const bf_handle* h) { return h ? h->N : 0; }

@@ -120,7 +120,7 @@ __global__ void __launch_bounds__(288) frames_kernel_1024(const KernelParams p) 
   SelScratch& sel = *reinterpret_cast<SelScratch*>(zall + (size_t)p.M * kXTile);
   constexpr bool kSel = (ALGO == ALGO_MVDR || ALGO == ALGO_LCMV || ALGO == ALGO_GSS);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
-  const int s = blockIdx.x;
+  const int s = blockIdx.x + p.stream_begin;
 
   for (int i = tid; i < 1024; i += blockDim.x) {
     int k1 = i >> 5, l = i & 31;
@@ -169,7 +169,7 @@ __global__ void __launch_bounds__(288) frames_kernel_1024(const KernelParams p) 
 
 // Saves the last hop of the call as "previous hop" state for the next call (util.h ring buffer).
 __global__ void save_prev_hop_kernel(const KernelParams p, int last_hop) {
-  const int s = blockIdx.y, ch = blockIdx.x;
+  const int s = blockIdx.y + p.stream_begin, ch = blockIdx.x;
   const float* src = p.in + (size_t)s * p.in_stream_stride + (size_t)ch * p.in_mic_stride + (size_t)last_hop * p.H;
   float* dst = p.prev_hop + ((size_t)s * p.M + ch) * p.H;
   for (int i = threadIdx.x; i < p.H; i += blockDim.x) dst[i] = src[i];

@@ -1,0 +1,290 @@
+#!/usr/bin/env python
+"""bench.py — beamformed audio-seconds per second on B200 (contract: see the task prompt / DESIGN.md).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload c2]
+
+A "step" is one pass of the fused hot path over one batch of synthetic multichannel audio
+(`--workload`): n_streams independent streams x hops_per_step hops, already resident in HBM.
+  value      whole-job audio-seconds / second over all ranks (device-resident inputs, CUDA events)
+  e2e        same metric through the host-buffer C-ABI call (pinned host -> H2D -> kernels -> D2H)
+  roofline   algorithmic bytes ((M+1)*4 B per sample) / measured kernel time, vs
+             MEASURED_PEAKS.json hbm_gbs
+  cpu_baseline   the CPU restatement of the reference (oracle/) on the host cores, bounded sample
+With --impl reference the same metric is measured for the reference's CPU path (oracle port: the
+original cannot be built here — FFTW/Eigen/JACK/ROS are absent) on all host threads.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from concurrent.futures import ThreadPoolExecutor
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import numpy as np
+
+SR = 48000
+H = 512
+
+WORKLOADS = {
+    # BASELINE.json configs[1]: the configuration the metric is quoted on
+    "c2": dict(name="C2: MVDR 8-mic 1024-pt, energy-thresholded bins, batched synthetic streams", algo="mvdr", mics="circ8",
+               n_streams=1024, hops_per_step=188, interferers=()),
+    "c1": dict(name="C1: DAS 3-mic (aira3) 1024-pt, batched synthetic streams", algo="das", mics="aira3", n_streams=2048,
+               hops_per_step=188, interferers=()),
+    "c3l": dict(name="C3: LCMV 8-mic, 3 interferers", algo="lcmv", mics="circ8", n_streams=1024, hops_per_step=188,
+                interferers=(80.0, -60.0, 150.0)),
+    "c3g": dict(name="C3: GSS 8-mic, 3 interferers", algo="gss", mics="circ8", n_streams=1024, hops_per_step=188,
+                interferers=(80.0, -60.0, 150.0)),
+}
+
+
+def device_synth(torch, mic_xy, n_streams, n_samples, seed, device):
+    """Synthetic plane-wave batch generated on the device (same signal model as beamform_b200.synth)."""
+    from beamform_b200.synth import mic_delays
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    rng = np.random.Generator(np.random.PCG64(seed))
+    M = len(mic_xy)
+    x = torch.empty((n_streams, M, n_samples), dtype=torch.float32, device=device)
+    n = torch.arange(n_samples, dtype=torch.float64, device=device) / SR
+    env = torch.ones(n_samples, dtype=torch.float64, device=device)
+    env[:2048] = 0.0
+    chunk = 32
+    for b0 in range(0, n_streams, chunk):
+        nb = min(chunk, n_streams - b0)
+        acc = 1e-3 * torch.randn((nb, M, n_samples), dtype=torch.float32, device=device, generator=g)
+        for (lo, hi, amp) in ((-40.0, 40.0, 0.1), (60.0, 300.0, 0.05)):
+            theta = rng.uniform(lo, hi, size=nb)
+            f0 = rng.uniform(120.0, 260.0, size=nb)
+            tau = np.stack([mic_delays(mic_xy, th) for th in theta])          # [nb][M]
+            tau_t = torch.tensor(tau, dtype=torch.float64, device=device)[:, :, None]
+            f0_t = torch.tensor(f0, dtype=torch.float64, device=device)[:, None, None]
+            t = n[None, None, :] - tau_t
+            s = torch.zeros((nb, M, n_samples), dtype=torch.float64, device=device)
+            for h in range(1, 13):
+                s += (1.0 / h) * torch.sin(2 * np.pi * h * f0_t * t + float(rng.uniform(0, 2 * np.pi)))
+            acc += (amp * env[None, None, :] * s).to(torch.float32)
+        x[b0:b0 + nb] = acc
+    return x
+
+
+class ClockSampler(threading.Thread):
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.max_mhz, self._halt = index, [], set(), None, threading.Event()
+
+    def run(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self._halt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip().split(",")
+                self.samples.append(float(out[0]))
+                self.max_mhz = float(out[1])
+                for nm, v in zip(names, out[2:]):
+                    if v.strip().lower().startswith("active"):
+                        self.reasons.add(nm)
+            except Exception:
+                pass
+            self._halt.wait(0.2)
+
+    def stop(self):
+        self._halt.set()
+        self.join(timeout=6)
+        return {"sm_mhz": float(np.median(self.samples)) if self.samples else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons)}
+
+
+def run_cpu_reference(cfg, mic_xy, n_sample_streams, hops, seed, threads):
+    """Times the CPU restatement (oracle/) on `threads` host threads: audio-seconds per second."""
+    from beamform_b200.synth import synth_batch
+    from oracle_lib import Oracle, lib as oracle_lib
+    oracle_lib()
+    x = synth_batch(mic_xy, n_sample_streams, hops * H, seed=seed)
+
+    def one(b):
+        Oracle(cfg).process(x[b])
+        return 0
+
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(max_workers=threads) as ex:
+        list(ex.map(one, range(n_sample_streams)))
+    dt = time.perf_counter() - t0
+    return n_sample_streams * hops * H / SR / dt, dt
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--streams", type=int, default=0, help="override streams per GPU")
+    ap.add_argument("--hops", type=int, default=0, help="override hops per step")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+
+    wl = dict(WORKLOADS[args.workload])
+    if args.streams:
+        wl["n_streams"] = args.streams
+    if args.hops:
+        wl["hops_per_step"] = args.hops
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    import beamform_b200 as bf
+    mic_xy = bf.GEOMETRIES[wl["mics"]]
+    M = len(mic_xy)
+    B, T = wl["n_streams"], wl["hops_per_step"]
+    cores = os.cpu_count() or 1
+    config = {"workload": wl["name"], "algo": wl["algo"], "n_mics": M, "fft_win": 2 * H, "hop": H, "sample_rate": SR,
+              "streams_per_gpu": B, "hops_per_step": T, "audio_s_per_step_per_gpu": B * T * H / SR,
+              "input_bytes_per_step_per_gpu": B * M * T * H * 4, "l2_policy": "inputs larger than L2 (126 MB), no flush"}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        cfg = bf.make_config(wl["algo"], mics=wl["mics"], interferers=wl["interferers"])
+        hops = 94
+        nstr = cores * 2
+        for _ in range(max(0, min(args.warmup, 1))):
+            run_cpu_reference(cfg, mic_xy, cores, 24, 5, cores)
+        vals, t_tot = [], 0.0
+        for k in range(args.steps):
+            v, dt = run_cpu_reference(cfg, mic_xy, nstr, hops, 100 + k, cores)
+            vals.append(v)
+            t_tot += dt
+        value = float(np.mean(vals))
+        sample = "%d streams x %d hops (%.1f s audio) per step on %d threads" % (nstr, hops, nstr * hops * H / SR, cores)
+        print(json.dumps({
+            "impl": "reference", "metric": "beamformed audio-sec/sec", "value": value, "unit": "audio-s/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_tot / max(1, args.steps), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
+            "cpu_baseline": {"value": value, "unit": "audio-s/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "note": "reference CPU path, restated (own FFT/LU in double; FFTW/Eigen/JACK/ROS are not installable here)"}))
+        return 0
+
+    import torch
+    import torch.distributed as dist
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    cfg = bf.make_config(wl["algo"], mics=wl["mics"], interferers=wl["interferers"], device=local_rank)
+    beam = bf.Beamformer(cfg, n_streams=B)
+    L = T * H
+    x = device_synth(torch, mic_xy, B, L, seed=0xBEA4F0 + 1000 * rank, device=dev)
+    y = torch.empty((B, L), dtype=torch.float32, device=dev)
+    stream = torch.cuda.current_stream()
+
+    def step():
+        beam.process_device(x.data_ptr(), y.data_ptr(), T, stream_ptr=stream.cuda_stream)
+
+    def fence():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    fence()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    beam.set_profiling(True)
+    l0 = beam.kernel_launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        step()
+    e1.record(stream)
+    fence()
+    clocks = sampler.stop()
+    elapsed_ms = e0.elapsed_time(e1)
+    launches = beam.kernel_launches - l0
+    kern_ms, kern_n = beam.get_profile()
+    beam.set_profiling(False)
+    t_max = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t_max, op=dist.ReduceOp.MAX)
+    elapsed_ms = float(t_max.item())
+    audio_s = world * B * L / SR * args.steps
+    value = audio_s / (elapsed_ms * 1e-3)
+
+    # ---- e2e: host buffers through the C ABI, H2D + kernels + D2H inside the timed region ----
+    e2e = None
+    if not args.no_e2e:
+        xh = torch.empty((B, M, L), dtype=torch.float32, pin_memory=True)
+        xh.copy_(x)
+        yh = torch.empty((B, L), dtype=torch.float32, pin_memory=True)
+        ev, nev = bf.make_events([])
+        lib = bf.lib()
+
+        def e2e_step():
+            rc = lib.bf_process_batch(beam._h, xh.data_ptr(), M * L, L, yh.data_ptr(), L, T, ev, nev)
+            assert rc == 0, lib.bf_last_error()
+
+        e2e_step()
+        fence()
+        n_e2e = max(1, min(args.steps, 3))
+        t0 = time.perf_counter()
+        for _ in range(n_e2e):
+            e2e_step()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        t_e = torch.tensor([dt], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
+        e2e = {"value": world * B * L / SR * n_e2e / float(t_e.item()), "unit": "audio-s/s", "h2d_bytes_per_step": B * M * L * 4,
+               "d2h_bytes_per_step": B * L * 4, "steps": n_e2e, "checksum": float(yh[:, -H:].double().abs().sum())}
+        del xh, yh
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        alg_bytes_per_launch = (M + 1) * 4.0 * B * L
+        achieved = alg_bytes_per_launch / (kern_ms / max(1, kern_n) * 1e-3) / 1e9 if kern_n else None
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic_%s.json" % args.workload))).get("dram_bytes_per_launch")
+        except Exception:
+            pass
+        cpu = None
+        if not args.no_cpu and world == 1:
+            nstr = cores * 2
+            v, dt = run_cpu_reference(cfg, mic_xy, nstr, 94, 77, cores)
+            cpu = {"value": v, "unit": "audio-s/s", "cores": cores, "kind": "port",
+                   "sample": "%d streams x 94 hops (%.1f s audio) of the same workload, %d threads, %.1f s wall" % (nstr, nstr * 94 * H / SR, cores, dt)}
+        out = {
+            "metric": "beamformed audio-sec/sec", "value": value, "unit": "audio-s/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32 (lcmv solves f64)" if wl["algo"] == "lcmv" else "f32", "data": "synthetic", "config": config,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
+                         "traffic": traffic, "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650",
+                         "kernel": "frames_kernel_1024<%s>" % wl["algo"], "kernel_ms_per_launch": kern_ms / max(1, kern_n),
+                         "algorithmic_bytes_per_launch": alg_bytes_per_launch},
+            "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
+        }
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -128,6 +128,12 @@ int bf_set_capture(bf_handle* h, uint8_t* dev_flags);
 int bf_srp_batch_device(bf_handle* h, const float* in_dev, size_t in_stream_stride, size_t in_mic_stride,
                         const float* thetas_deg_host, uint32_t n_dirs, float* maps_dev, uint32_t n_hops, void* cuda_stream);
 
+/* --- measurement: when enabled, CUDA events bracket every launch of the fused frames kernel on the
+ *     launching stream; bf_get_profile() synchronises them and returns the summed device time (ms) and
+ *     the number of launches since the last call. -------------------------------------------------- */
+int bf_set_profiling(bf_handle* h, int enabled);
+int bf_get_profile(bf_handle* h, double* kernel_ms, uint64_t* kernel_launches);
+
 /* --- introspection ------------------------------------------------------------------------- */
 uint32_t bf_fft_win(const bf_handle* h);
 uint64_t bf_kernel_launches(const bf_handle* h);   /* kernels launched so far by this handle */
