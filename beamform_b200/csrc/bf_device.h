@@ -51,6 +51,8 @@ struct KernelParams {
   float min_mag;            // phasempf
   const double* win_d;      // [N] sqrt-hann in double, for FP64 rechecks
   const double2* twid_d;    // [N] e^{-2 pi i k/N} in double, for FP64 rechecks
+  const double2* steer_d;   // [L][M] look-direction steering in double (phase family rechecks)
+  double mag_threshold_d, min_phase_rad_d;
   // phasempf state, [B][7][L] floats: S_prev, S_tmp, S_min, lambda_noise, Z, rev0, rev1
   float* mpf_state;
   float mcra_alphaS, mcra_alphaD, mcra_alphaD2, mcra_delta;

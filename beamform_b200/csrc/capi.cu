@@ -81,6 +81,10 @@ struct bf_handle {
   float2* d_gss_w = nullptr;    // gss: [B][Lsel][C][M]
   double* d_win_d = nullptr;
   double2* d_twid_d = nullptr;
+  double2* d_steer_d = nullptr;   // phase family: [L][M] look-direction steering in double
+  float* d_mpf_state = nullptr;   // phasempf: [B][7][L]
+  float* d_smooth_hist = nullptr; // phasempf: [B][64]
+  int mcra_cur_L = 0, mcra_first = 1;   // phasempf.cpp:47-48
   bool gss_reset_pending = true;
   // host-batch staging + copy/compute overlap
   float* d_io_in = nullptr;
@@ -309,6 +313,13 @@ static int upload_tables(bf_handle* h, cudaStream_t st) {
       }
     CUDA_TRY(cudaMemcpyAsync(h->d_das_ceff, ceff.data(), sizeof(float2) * ceff.size(), cudaMemcpyHostToDevice, st));
   }
+  if (h->d_steer_d) {
+    std::vector<double2> sd((size_t)L * M);
+    for (uint32_t l = 0; l < L; l++)
+      for (uint32_t i = 0; i < M; i++) { cd w = W(h, l, i, 0); sd[(size_t)l * M + i] = make_double2(w.real(), w.imag()); }
+    CUDA_TRY(cudaMemcpyAsync(h->d_steer_d, sd.data(), sizeof(double2) * sd.size(), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+  }
   std::vector<uint8_t> inband(L);
   for (uint32_t l = 0; l < L; l++) {
     double f = std::fabs(h->freqs[bin_of_logical(h, l)]);   // mvdr.cpp:78,84
@@ -386,8 +397,22 @@ extern "C" int bf_create(bf_handle** out, const bf_config* cfg, uint32_t n_strea
     }
     h->Lsel = (int)list.size();
     const bool sel_algo = cfg->algo == BF_ALGO_MVDR || cfg->algo == BF_ALGO_LCMV || cfg->algo == BF_ALGO_GSS;
-    if (sel_algo) {
-      if ((cfg->algo != BF_ALGO_GSS) && h->M > 8) { bf_destroy(h); return fail(BF_ERR_INVALID, "bf_create: mvdr/lcmv support at most 8 microphones in this build"); }
+    const bool pha_algo = cfg->algo == BF_ALGO_PHASE || cfg->algo == BF_ALGO_PHASEMPF;
+    if (pha_algo) {
+      if (cfg->algo == BF_ALGO_PHASEMPF && (cfg->smooth_size < 1 || cfg->smooth_size > 64)) {
+        bf_destroy(h);
+        return fail(BF_ERR_INVALID, "bf_create: smooth_size must be in [1, 64]");
+      }
+      const size_t ns = (size_t)h->B * 7 * h->L;
+      bool ok3 = cudaMalloc(&h->d_steer_d, sizeof(double2) * h->L * h->M) == cudaSuccess &&
+                 cudaMalloc(&h->d_mpf_state, sizeof(float) * ns) == cudaSuccess &&
+                 cudaMalloc(&h->d_smooth_hist, sizeof(float) * h->B * 64) == cudaSuccess;
+      if (!ok3) { bf_destroy(h); return fail(BF_ERR_ALLOC, "bf_create: device allocation failed (phase state)"); }
+      cudaMemset(h->d_mpf_state, 0, sizeof(float) * ns);              // phasempf.cpp:535-545
+      cudaMemset(h->d_smooth_hist, 0, sizeof(float) * h->B * 64);     // phasempf.cpp:510 calloc
+    }
+    if (sel_algo || pha_algo) {
+      if ((cfg->algo == BF_ALGO_MVDR || cfg->algo == BF_ALGO_LCMV) && h->M > 8) { bf_destroy(h); return fail(BF_ERR_INVALID, "bf_create: mvdr/lcmv support at most 8 microphones in this build"); }
       if (cfg->past_windows < 1) { bf_destroy(h); return fail(BF_ERR_INVALID, "bf_create: past_windows must be >= 1"); }
       std::vector<double> win(h->N);
       std::vector<double2> twd(h->N);
@@ -399,7 +424,7 @@ extern "C" int bf_create(bf_handle** out, const bf_config* cfg, uint32_t n_strea
       const size_t nl = std::max(1, h->Lsel);
       bool ok2 = cudaMalloc(&h->d_sel_slot, sizeof(int) * h->L) == cudaSuccess && cudaMalloc(&h->d_sel_list, sizeof(int) * nl) == cudaSuccess &&
                  cudaMalloc(&h->d_win_d, sizeof(double) * h->N) == cudaSuccess && cudaMalloc(&h->d_twid_d, sizeof(double2) * h->N) == cudaSuccess;
-      if (ok2 && cfg->algo != BF_ALGO_GSS) {
+      if (ok2 && (cfg->algo == BF_ALGO_MVDR || cfg->algo == BF_ALGO_LCMV)) {
         const size_t nh = (size_t)h->B * nl * cfg->past_windows * h->M;
         ok2 = cudaMalloc(&h->d_hist, sizeof(float2) * nh) == cudaSuccess;
         if (ok2) cudaMemset(h->d_hist, 0, sizeof(float2) * nh);   // past_ffts.setZero() (mvdr.cpp:229-233)
@@ -429,6 +454,7 @@ extern "C" void bf_destroy(bf_handle* h) {
   if (h->st_h2d) cudaStreamDestroy(h->st_h2d);
   if (h->st_d2h) cudaStreamDestroy(h->st_d2h);
   for (int i = 0; i < 8; i++) { if (h->ev_in[i]) cudaEventDestroy(h->ev_in[i]); if (h->ev_k[i]) cudaEventDestroy(h->ev_k[i]); }
+  cudaFree(h->d_steer_d); cudaFree(h->d_mpf_state); cudaFree(h->d_smooth_hist);
   cudaFree(h->d_sel_slot); cudaFree(h->d_sel_list); cudaFree(h->d_hist); cudaFree(h->d_gss_w); cudaFree(h->d_win_d); cudaFree(h->d_twid_d);
   if (h->h_stage_in) cudaFreeHost(h->h_stage_in);
   if (h->h_stage_out) cudaFreeHost(h->h_stage_out);
@@ -554,7 +580,21 @@ static int run_segment(bf_handle* h, const float* in, size_t ss, size_t ms, floa
   p.lambda_mu = (float)(1 - h->cfg.lambda * h->cfg.mu);
   p.gss_w = h->d_gss_w;
   p.gss_dj2_scale = (float)(2 * (1 / (size_t)h->C));   // gss.cpp:133: integer arithmetic (SURVEY B-7)
-  p.win_d = h->d_win_d; p.twid_d = h->d_twid_d;
+  p.win_d = h->d_win_d; p.twid_d = h->d_twid_d; p.steer_d = h->d_steer_d;
+  p.mag_threshold_d = h->cfg.mag_threshold;
+  p.min_phase_rad_d = h->cfg.min_phase * M_PI / 180;   // phase.cpp:175
+  p.min_phase_rad = (float)p.min_phase_rad_d;
+  p.thr_phase_mag = (float)(h->cfg.mag_threshold * (double)h->M * (double)h->N);
+  p.mag_mult = (float)h->cfg.mag_mult;
+  p.min_mag = (float)h->cfg.min_mag;
+  p.mpf_state = h->d_mpf_state; p.smooth_hist = h->d_smooth_hist; p.smooth_size = h->cfg.smooth_size;
+  p.mcra_alphaS = (float)h->cfg.MCRA_alphaS; p.mcra_alphaD = (float)h->cfg.MCRA_alphaD;
+  p.mcra_alphaD2 = (float)h->cfg.MCRA_alphaD2; p.mcra_delta = (float)h->cfg.MCRA_delta;
+  p.mcra_L = h->cfg.MCRA_L; p.mcra_cur_L0 = h->mcra_cur_L; p.mcra_first0 = h->mcra_first;
+  p.mpf_alphaS = (float)h->cfg.MPF_alphaS; p.mpf_eta = (float)h->cfg.MPF_eta; p.mpf_gamma = (float)h->cfg.MPF_rev_gamma;
+  p.mpf_rev_gain = (float)(1 - h->cfg.MPF_rev_gamma / h->cfg.MPF_rev_delta);   // phasempf.cpp:265-266
+  p.out_amp = (float)h->cfg.out_amp; p.noise_floor = (float)h->cfg.noise_floor;
+  p.out_only_noise = h->cfg.out_only_noise; p.out_only_mcra = h->cfg.out_only_mcra;
   if (h->cfg.algo == BF_ALGO_GSS && h->gss_reset_pending) {
     bf::KernelParams pr = p;
     pr.n_streams = h->B; pr.stream_begin = 0;
@@ -575,7 +615,13 @@ static int run_segment(bf_handle* h, const float* in, size_t ss, size_t ms, floa
   }
   CUDA_TRY(bf::launch_save_prev_hop(p, (int)(h1 - h0) - 1, st));
   h->launches += 2;
-  if (s0 + p.n_streams >= h->B) h->frames_done += h1 - h0;   // the last stream chunk closes the segment
+  if (s0 + p.n_streams >= h->B) {   // the last stream chunk closes the segment
+    h->frames_done += h1 - h0;
+    if (h->cfg.algo == BF_ALGO_PHASEMPF)
+      for (uint32_t t = h0; t < h1; t++) {   // phasempf.cpp:162-176: window counters advance once per frame
+        if (h->mcra_cur_L > h->cfg.MCRA_L) { h->mcra_cur_L = 1; h->mcra_first = 0; } else h->mcra_cur_L++;
+      }
+  }
   return BF_OK;
 }
 

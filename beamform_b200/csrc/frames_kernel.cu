@@ -14,6 +14,7 @@
 #include "bf_device.h"
 #include "warp_fft1024.cuh"
 #include "phase_b_select.cuh"
+#include "phase_b_phase.cuh"
 
 namespace bf {
 
@@ -70,27 +71,49 @@ __device__ __forceinline__ void forward_mic(const KernelParams& p, int s, int ch
 // y_t = Re(IFFT(G)), y_{t+1} = Im(IFFT(G)).  tail[] holds out_buff[0][j+H] of the previous frame for
 // j = lane + 32*m2; each lane owns the same sample columns in every iteration, so the OLA never leaves
 // registers.  out hop t = tail + y_t[:H]; out hop t+1 = y_t[H:] + y_{t+1}[:H].
+template <bool SMOOTH>
 __device__ __forceinline__ void inverse_pair(const KernelParams& p, int s, PairCtx pc, const float2* g, float2* tile,
-                                             const float2* tw, int lane, float s_o, float c_o, float (&tail)[16]) {
+                                             const float2* tw, int lane, float s_o, float c_o, float (&tail)[16], float* ola) {
   float2 v[32];
   static_for<0, 32>([&](auto j1) { v[brev5(j1)] = g[j1 * 32 + lane]; });
   __syncwarp();
   warp_fft1024<1>(v, tile, tw, lane);
   float* o0 = p.out + (size_t)s * p.out_stream_stride + (size_t)pc.t * p.H;
   float* o1 = o0 + p.H;
+  const int S1 = SMOOTH ? p.smooth_size - 1 : 0;
   static_for<0, 16>([&](auto m2) {
     const float w0 = win1024<m2>(s_o, c_o);
     const float w1 = win1024<m2 + 16>(s_o, c_o);
     const float y0a = v[m2].x * w0, y0b = v[m2 + 16].x * w1;     // frame t: first / second half
     const float y1a = v[m2].y * w0, y1b = v[m2 + 16].y * w1;     // frame t+1
-    o0[32 * m2 + lane] = tail[m2] + y0a;
+    const float r0 = tail[m2] + y0a;
+    if (SMOOTH) ola[S1 + 32 * m2 + lane] = r0; else o0[32 * m2 + lane] = r0;
     if (pc.two) {
-      o1[32 * m2 + lane] = y0b + y1a;
+      const float r1 = y0b + y1a;
+      if (SMOOTH) ola[S1 + 512 + 32 * m2 + lane] = r1; else o1[32 * m2 + lane] = r1;
       tail[m2] = y1b;
     } else {
       tail[m2] = y0b;
     }
   });
+  if (SMOOTH) {
+    // phasempf.cpp:78-83,122-130,331-334: every output sample becomes the mean of the last smooth_size
+    // OLA samples (double accumulation, zero-initialised history carried in ola[0 .. smooth_size-2])
+    __syncwarp();
+    const int cnt = pc.two ? 1024 : 512, S = p.smooth_size;
+    const double inv = 1.0 / (double)S;
+    for (int n = lane; n < cnt; n += 32) {
+      double acc = 0.0;
+      for (int k = 0; k < S; k++) acc += (double)ola[n + k];
+      o0[n] = (float)(acc * inv);
+    }
+    __syncwarp();
+    float keep[2];
+    for (int i = lane, q = 0; i < S1; i += 32, q++) keep[q] = ola[cnt + i];
+    __syncwarp();
+    for (int i = lane, q = 0; i < S1; i += 32, q++) ola[i] = keep[q];
+    __syncwarp();
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -118,7 +141,13 @@ __global__ void __launch_bounds__(288) frames_kernel_1024(const KernelParams p) 
   float2* gbuf = tw + 1024;                                // G, then warp 0's exchange tile
   float2* zall = gbuf + kXTile;                            // [M] tiles: exchange tile, then Z linear
   SelScratch& sel = *reinterpret_cast<SelScratch*>(zall + (size_t)p.M * kXTile);
+  PhaseScratch& phs = *reinterpret_cast<PhaseScratch*>(zall + (size_t)p.M * kXTile);
   constexpr bool kSel = (ALGO == ALGO_MVDR || ALGO == ALGO_LCMV || ALGO == ALGO_GSS);
+  constexpr bool kPha = (ALGO == ALGO_PHASE || ALGO == ALGO_PHASEMPF);
+  constexpr bool kSmooth = (ALGO == ALGO_PHASEMPF);
+  float* sqrtE0 = kSel ? sel.sqrtE[0] : phs.sqrtE[0];
+  float* sqrtE1 = kSel ? sel.sqrtE[1] : phs.sqrtE[1];
+  int cur_L = p.mcra_cur_L0, first_L = p.mcra_first0;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
   const int s = blockIdx.x + p.stream_begin;
 
@@ -136,7 +165,11 @@ __global__ void __launch_bounds__(288) frames_kernel_1024(const KernelParams p) 
   if (warp == 0) {
 #pragma unroll
     for (int m2 = 0; m2 < 16; m2++) tail[m2] = p.tail[(size_t)s * p.H + 32 * m2 + lane];
+    if (kSmooth)
+      for (int i = lane; i < p.smooth_size - 1; i += 32) phs.ola[i] = p.smooth_hist[(size_t)s * 64 + i];
   }
+  if (ALGO == ALGO_PHASEMPF)
+    for (int i = tid; i < 7 * kL1K; i += blockDim.x) (&phs.state[0][0])[i] = p.mpf_state[(size_t)s * 7 * kL1K + i];
   __syncthreads();
 
   const int npairs = (p.hop_end - p.hop_begin + 1) / 2;
@@ -149,21 +182,28 @@ __global__ void __launch_bounds__(288) frames_kernel_1024(const KernelParams p) 
         PairCtx pv;
         pv.t = pc.t - 2;
         pv.two = pv.t + 1 < p.hop_end;
-        inverse_pair(p, s, pv, gbuf, gbuf, tw, lane, s_o, c_o, tail);
+        inverse_pair<kSmooth>(p, s, pv, gbuf, gbuf, tw, lane, s_o, c_o, tail, phs.ola);
       }
     } else if (ip < npairs) {
       for (int ch = warp - 1; ch < p.M; ch += nwarps - 1)
-        forward_mic<kSel>(p, s, ch, pc, zall + ch * kXTile, tw, lane, s_l, c_l, sel.sqrtE[0], sel.sqrtE[1]);
+        forward_mic<kSel || kPha>(p, s, ch, pc, zall + ch * kXTile, tw, lane, s_l, c_l, sqrtE0, sqrtE1);
     }
     if (ip == npairs) break;
     __syncthreads();   // Z complete; previous G consumed
     if (ALGO == ALGO_DAS) phase_b_das(p, zall, gbuf, tid, blockDim.x);
     if (kSel) phase_b_select<ALGO>(p, s, pc.t, pc.two, zall, gbuf, sel, tid, blockDim.x);
+    if (kPha) phase_b_phase<ALGO>(p, s, pc.t, pc.two, zall, gbuf, phs, cur_L, first_L, tid, blockDim.x);
     __syncthreads();   // G complete; Z consumed
   }
   if (warp == 0) {
 #pragma unroll
     for (int m2 = 0; m2 < 16; m2++) p.tail[(size_t)s * p.H + 32 * m2 + lane] = tail[m2];
+    if (kSmooth)
+      for (int i = lane; i < p.smooth_size - 1; i += 32) p.smooth_hist[(size_t)s * 64 + i] = phs.ola[i];
+  }
+  if (ALGO == ALGO_PHASEMPF) {
+    __syncthreads();
+    for (int i = tid; i < 7 * kL1K; i += blockDim.x) p.mpf_state[(size_t)s * 7 * kL1K + i] = (&phs.state[0][0])[i];
   }
 }
 
@@ -192,7 +232,7 @@ cudaError_t launch_gss_reset(const KernelParams& p, cudaStream_t st) {
   return cudaGetLastError();
 }
 
-size_t frames_kernel_smem(int M) { return sizeof(float2) * (1024 + (size_t)kXTile * (1 + M)) + sizeof(SelScratch); }
+size_t frames_kernel_smem(int M) { return sizeof(float2) * (1024 + (size_t)kXTile * (1 + M)) + (sizeof(SelScratch) > sizeof(PhaseScratch) ? sizeof(SelScratch) : sizeof(PhaseScratch)); }
 
 cudaError_t launch_frames_kernel_1024(int algo, const KernelParams& p, cudaStream_t st) {
   const int fwd = p.M < 8 ? p.M : 8;
@@ -204,6 +244,8 @@ cudaError_t launch_frames_kernel_1024(int algo, const KernelParams& p, cudaStrea
     case ALGO_MVDR: k = frames_kernel_1024<ALGO_MVDR>; break;
     case ALGO_LCMV: k = frames_kernel_1024<ALGO_LCMV>; break;
     case ALGO_GSS: k = frames_kernel_1024<ALGO_GSS>; break;
+    case ALGO_PHASE: k = frames_kernel_1024<ALGO_PHASE>; break;
+    case ALGO_PHASEMPF: k = frames_kernel_1024<ALGO_PHASEMPF>; break;
     default: return cudaErrorNotSupported;
   }
   cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
