@@ -26,6 +26,8 @@ cudaError_t launch_frames_kernel_1024(int algo, const KernelParams& p, cudaStrea
 cudaError_t launch_save_prev_hop(const KernelParams& p, int last_hop, cudaStream_t st);
 cudaError_t launch_gss_reset(const KernelParams& p, cudaStream_t st);
 size_t frames_kernel_smem(int M);
+bool das_pairs_supported(const KernelParams& p);
+cudaError_t launch_das_pairs(const KernelParams& p, cudaStream_t st, int sm_count);
 }   // namespace bf
 
 typedef std::complex<double> cd;
@@ -69,6 +71,7 @@ struct bf_handle {
   // ---- device ----
   float* d_prev_hop = nullptr;
   float* d_tail = nullptr;
+  int sm_count = 148;
   float2* d_steer = nullptr;
   float2* d_das_ceff = nullptr;
   uint8_t* d_inband = nullptr;
@@ -350,6 +353,7 @@ extern "C" int bf_create(bf_handle** out, const bf_config* cfg, uint32_t n_strea
   CUDA_TRY(cudaSetDevice(cfg->device));
 
   bf_handle* h = new bf_handle();
+  h->sm_count = prop.multiProcessorCount;
   h->cfg = *cfg;
   h->dev = cfg->device;
   h->B = n_streams; h->M = cfg->n_mics; h->H = cfg->hop; h->N = 2 * cfg->hop; h->L = h->N / 2 + 2;
@@ -608,7 +612,8 @@ static int run_segment(bf_handle* h, const float* in, size_t ss, size_t ms, floa
     CUDA_TRY(cudaEventCreate(&ev1));
     CUDA_TRY(cudaEventRecord(ev0, st));
   }
-  CUDA_TRY(bf::launch_frames_kernel_1024(h->cfg.algo, p, st));
+  if (h->cfg.algo == BF_ALGO_DAS && bf::das_pairs_supported(p)) CUDA_TRY(bf::launch_das_pairs(p, st, h->sm_count));
+  else CUDA_TRY(bf::launch_frames_kernel_1024(h->cfg.algo, p, st));
   if (h->profiling) {
     CUDA_TRY(cudaEventRecord(ev1, st));
     h->prof_events.push_back(std::make_pair(ev0, ev1));
