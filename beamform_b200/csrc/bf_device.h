@@ -40,12 +40,14 @@ struct KernelParams {
   float thr_mag;            // freq_mag_threshold * M * N   (gate compares sum_i |X_i| directly)
   double thr_mag_d;         // exact double threshold for the FP64 recheck
   int P;                    // past_windows
-  float2* hist;             // [B][Lsel][P][M]  mvdr/lcmv history ring, slot = frame % P
+  float2* hist;             // [B][D][M][Lsel]  mvdr/lcmv history ring (bin fastest), D = ring_depth = P + 2, slot = frame % D
+  int debug;                // profiling experiments only (env BF_DEBUG): 0 in production
+  int ring_depth, ring_slot0;   // ring_slot0 = slot of hop 0 of this launch
   const int* sel_slot;      // [L] -> slot in the in-band compact list or -1
   const int* sel_list;      // [Lsel] -> logical bin
   int Lsel;
   float mu, lambda_mu;      // gss: mu, (1 - lambda*mu)
-  float2* gss_w;            // [B][Lsel][C][M]
+  float2* gss_w;            // [B][8][M][Lsel] (bin fastest)
   float gss_dj2_scale;      // 2 * (1/(K+1)) in integer arithmetic (gss.cpp:133) -> 2 for K=0 else 0
   float min_phase_rad, mag_mult, thr_phase_mag;   // phase
   float min_mag;            // phasempf

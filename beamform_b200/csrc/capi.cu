@@ -28,6 +28,8 @@ cudaError_t launch_gss_reset(const KernelParams& p, cudaStream_t st);
 size_t frames_kernel_smem(int M);
 bool das_pairs_supported(const KernelParams& p);
 cudaError_t launch_das_pairs(const KernelParams& p, cudaStream_t st, int sm_count);
+bool sel_pairs_supported(const KernelParams& p, int algo);
+cudaError_t launch_sel_pairs(int algo, const KernelParams& p, cudaStream_t st);
 }   // namespace bf
 
 typedef std::complex<double> cd;
@@ -80,7 +82,7 @@ struct bf_handle {
   int* d_sel_slot = nullptr;
   int* d_sel_list = nullptr;
   int Lsel = 0;
-  float2* d_hist = nullptr;     // mvdr/lcmv: [B][Lsel][P][M]
+  float2* d_hist = nullptr;     // mvdr/lcmv: [B][Lsel][P+2][M]
   float2* d_gss_w = nullptr;    // gss: [B][Lsel][C][M]
   double* d_win_d = nullptr;
   double2* d_twid_d = nullptr;
@@ -429,7 +431,7 @@ extern "C" int bf_create(bf_handle** out, const bf_config* cfg, uint32_t n_strea
       bool ok2 = cudaMalloc(&h->d_sel_slot, sizeof(int) * h->L) == cudaSuccess && cudaMalloc(&h->d_sel_list, sizeof(int) * nl) == cudaSuccess &&
                  cudaMalloc(&h->d_win_d, sizeof(double) * h->N) == cudaSuccess && cudaMalloc(&h->d_twid_d, sizeof(double2) * h->N) == cudaSuccess;
       if (ok2 && (cfg->algo == BF_ALGO_MVDR || cfg->algo == BF_ALGO_LCMV)) {
-        const size_t nh = (size_t)h->B * nl * cfg->past_windows * h->M;
+        const size_t nh = (size_t)h->B * nl * (cfg->past_windows + 2) * h->M;
         ok2 = cudaMalloc(&h->d_hist, sizeof(float2) * nh) == cudaSuccess;
         if (ok2) cudaMemset(h->d_hist, 0, sizeof(float2) * nh);   // past_ffts.setZero() (mvdr.cpp:229-233)
       }
@@ -579,6 +581,9 @@ static int run_segment(bf_handle* h, const float* in, size_t ss, size_t ms, floa
   p.thr_mag = (float)(h->cfg.freq_mag_threshold * (double)h->M * (double)h->N);
   p.thr_mag_d = h->cfg.freq_mag_threshold;
   p.P = (int)h->cfg.past_windows;
+  { static const int dbg = getenv("BF_DEBUG") ? atoi(getenv("BF_DEBUG")) : 0; p.debug = dbg; }
+  p.ring_depth = (int)h->cfg.past_windows + 2;
+  p.ring_slot0 = (int)(h->frames_done % (uint64_t)p.ring_depth);
   p.hist = h->d_hist; p.sel_slot = h->d_sel_slot; p.sel_list = h->d_sel_list; p.Lsel = h->Lsel;
   p.mu = (float)h->cfg.mu;
   p.lambda_mu = (float)(1 - h->cfg.lambda * h->cfg.mu);
@@ -613,6 +618,7 @@ static int run_segment(bf_handle* h, const float* in, size_t ss, size_t ms, floa
     CUDA_TRY(cudaEventRecord(ev0, st));
   }
   if (h->cfg.algo == BF_ALGO_DAS && bf::das_pairs_supported(p)) CUDA_TRY(bf::launch_das_pairs(p, st, h->sm_count));
+  else if (bf::sel_pairs_supported(p, h->cfg.algo)) CUDA_TRY(bf::launch_sel_pairs(h->cfg.algo, p, st));
   else CUDA_TRY(bf::launch_frames_kernel_1024(h->cfg.algo, p, st));
   if (h->profiling) {
     CUDA_TRY(cudaEventRecord(ev1, st));

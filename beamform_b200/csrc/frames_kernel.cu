@@ -217,14 +217,15 @@ __global__ void save_prev_hop_kernel(const KernelParams p, int last_hop) {
 
 // gss.cpp:90-93: every update_weights resets sep_matrix[j] = weights[j]^H (adaptation is discarded)
 __global__ void gss_reset_kernel(const KernelParams p) {
-  const size_t per = (size_t)p.Lsel * p.C * p.M;
+  // state layout [B][8][M][Lsel] (bin fastest); only the first C rows are live
+  const size_t per = (size_t)p.C * p.M * p.Lsel;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < (size_t)p.n_streams * per; i += (size_t)gridDim.x * blockDim.x) {
-    const size_t r = i % per;
-    const int slot = (int)(r / ((size_t)p.C * p.M));
-    const int c = (int)((r / p.M) % p.C), m = (int)(r % p.M);
+    const size_t sidx = i / per, r = i % per;
+    const int slot = (int)(r % p.Lsel);
+    const int cm = (int)(r / p.Lsel), c = cm / p.M, m = cm % p.M;
     const int l = p.sel_list[slot];
     const float2 a = p.steer[((size_t)l * p.C + c) * p.M + m];
-    p.gss_w[i] = make_float2(a.x, -a.y);
+    p.gss_w[sidx * 8 * p.M * p.Lsel + (size_t)cm * p.Lsel + slot] = make_float2(a.x, -a.y);
   }
 }
 cudaError_t launch_gss_reset(const KernelParams& p, cudaStream_t st) {
@@ -241,8 +242,6 @@ cudaError_t launch_frames_kernel_1024(int algo, const KernelParams& p, cudaStrea
   void (*k)(KernelParams) = nullptr;
   switch (algo) {
     case ALGO_DAS: k = frames_kernel_1024<ALGO_DAS>; break;
-    case ALGO_MVDR: k = frames_kernel_1024<ALGO_MVDR>; break;
-    case ALGO_LCMV: k = frames_kernel_1024<ALGO_LCMV>; break;
     case ALGO_GSS: k = frames_kernel_1024<ALGO_GSS>; break;
     case ALGO_PHASE: k = frames_kernel_1024<ALGO_PHASE>; break;
     case ALGO_PHASEMPF: k = frames_kernel_1024<ALGO_PHASEMPF>; break;

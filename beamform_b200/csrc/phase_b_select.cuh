@@ -255,9 +255,10 @@ __device__ __forceinline__ float2 lcmv_item(const KernelParams& p, const float2*
   return make_float2((float)y.x, (float)y.y);
 }
 
-// gss.cpp:118-137 for one selected frame of one bin; W (C x M, row-major [c][i]) lives in global memory
-// (L2-resident between frames).  Returns y_0.
-__device__ __forceinline__ float2 gss_item(const KernelParams& p, float2* Wg, const float2* x, const float2* steer_l) {
+// gss.cpp:118-137 for one selected frame of one bin; W (C x M) lives in global memory (L2-resident between
+// frames), element (c, i) at Wg[(c*M + i) * ws]: the bin index is the fastest axis of the state array so that
+// neighbouring threads (= neighbouring bins) touch neighbouring addresses.  Returns y_0.
+__device__ __forceinline__ float2 gss_item(const KernelParams& p, float2* Wg, size_t ws, const float2* x, const float2* steer_l) {
   const int C = p.C, M = p.M;
   float2 y[kMaxC];
   float alpha = 0.f;
@@ -265,7 +266,7 @@ __device__ __forceinline__ float2 gss_item(const KernelParams& p, float2* Wg, co
   alpha *= alpha;
   for (int c = 0; c < C; c++) {
     float2 acc = make_float2(0.f, 0.f);
-    for (int i = 0; i < M; i++) acc = cadd(acc, cmul(Wg[c * M + i], x[i]));
+    for (int i = 0; i < M; i++) acc = cadd(acc, cmul(Wg[(size_t)(c * M + i) * ws], x[i]));
     y[c] = acc;
   }
   // (E y)_r = sum_{c != r} y_r conj(y_c) y_c = y_r * (sum_c |y_c|^2 - |y_r|^2)   (gss.cpp:124-125)
@@ -279,7 +280,7 @@ __device__ __forceinline__ float2 gss_item(const KernelParams& p, float2* Wg, co
     if (p.gss_dj2_scale != 0.f) {   // (W A - I) row r; only K = 0 keeps the geometric term (gss.cpp:133, integer 1/(K+1))
       for (int c = 0; c < C; c++) {
         float2 acc = make_float2(c == r ? -1.f : 0.f, 0.f);
-        for (int i = 0; i < M; i++) acc = cadd(acc, cmul(Wg[r * M + i], steer_l[(size_t)c * M + i]));
+        for (int i = 0; i < M; i++) acc = cadd(acc, cmul(Wg[(size_t)(r * M + i) * ws], steer_l[(size_t)c * M + i]));
         wa[c] = acc;
       }
     }
@@ -291,10 +292,10 @@ __device__ __forceinline__ float2 gss_item(const KernelParams& p, float2* Wg, co
         dj.x += p.gss_dj2_scale * acc.x;
         dj.y += p.gss_dj2_scale * acc.y;
       }
-      float2 w = Wg[r * M + i];
+      float2 w = Wg[(size_t)(r * M + i) * ws];
       w.x = p.lambda_mu * w.x - p.mu * dj.x;   // gss.cpp:136
       w.y = p.lambda_mu * w.y - p.mu * dj.y;
-      Wg[r * M + i] = w;
+      Wg[(size_t)(r * M + i) * ws] = w;
     }
   }
   return y[0];
@@ -391,12 +392,12 @@ __device__ __forceinline__ void phase_b_select(const KernelParams& p, int s, int
     const int slot = p.sel_slot[l];
     const float2* steer_l = p.steer + (size_t)l * p.C * M;
     if (ALGO == ALGO_GSS) {
-      float2* Wg = p.gss_w + ((size_t)s * p.Lsel + slot) * p.C * M;
+      float2* Wg = p.gss_w + (size_t)s * 8 * M * p.Lsel + slot;   // [B][8][M][Lsel]
       for (int ff = 0; ff < nf; ff++) {
         if (!sc.flag[ff][l]) continue;
         float2 x[BF_MAX_MICS_DEV];
         for (int ch = 0; ch < M; ch++) x[ch] = unpack_bin(zall + ch * kXTile, l, ff);
-        sc.y[ff][l] = gss_item(p, Wg, x, steer_l);
+        sc.y[ff][l] = gss_item(p, Wg, (size_t)p.Lsel, x, steer_l);
       }
     } else {
       float2 x[kMaxMSel], xprev[kMaxMSel];

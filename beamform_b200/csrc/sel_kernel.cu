@@ -1,0 +1,531 @@
+// Fused kernel for the magnitude-gated nodes (mvdr / lcmv / gss), 1024-point frames, M <= 8, sm_100a.
+//
+//   reference path replaced (citations /root/reference/beamform/src/): util.h:217-253,289-314 (window, framing,
+//   OLA) and apply_weights of mvdr.cpp:62-115, lcmv.cpp:88-140, gss.cpp:96-156.
+//
+// One CTA (8 warps) owns one stream and walks its frame pairs (t, t+1) in order; two CTAs share an SM (96 KB of
+// shared memory and <= 128 registers per thread each) so one CTA's latency-bound phase overlaps the other's math:
+//   A   warp w: hops t-1..t+1 of microphone w arrive in its (then idle) spectrum tile by TMA bulk copy, issued as
+//       soon as the previous pair's solves are done; window -> packed 1024-point FFT (registers + one swizzled
+//       shared-memory transpose) -> Z_w in the same tile
+//   B1  thread per logical bin: even/odd separation of every microphone's packed spectrum into X_t, X_{t+1}, FP32
+//       magnitude gate with a guard band, append both frames to the per-stream history ring (global, L2-resident:
+//       ring depth P+2 so a pair's two appends never overwrite a frame its own solves still need), default outputs
+//   B1b guarded bins are re-decided in FP64 (exact double DFT of that bin) -> bit-exact selected-bin set
+//   B2  thread per selected (bin, frame): covariance of the previous P frames, Cholesky, MVDR / LCMV weights (or
+//       the GSS recursion, thread per bin); the LAST warp first runs the inverse FFT + overlap-add of the PREVIOUS
+//       pair, which hides the one transform that has no peer inside the solves' slack
+//   B3  Hermitian assembly of G = Yh_t + i*Yh_{t+1} for the next inverse
+// Spectra never leave the SM except for the history ring the algorithm itself keeps (mvdr.cpp:99-101).
+#include <cstdlib>
+
+#include "async_copy.cuh"
+#include "bf_device.h"
+#include "fft_reg.cuh"
+#include "warp_fft1024.cuh"
+#include "phase_b_select.cuh"
+
+namespace bf {
+
+constexpr int kSelWarps = 8;
+constexpr int kSelThreads = kSelWarps * 32;
+
+// forward 1024-point FFT, same compact form as das_kernel.cu (one copy of the butterfly code, swizzled 8 KB tile)
+__device__ __forceinline__ void sel_fft1024_fwd(float2 (&v)[32], float2* tile, const float2* __restrict__ tw, int lane) {
+#pragma unroll 1
+  for (int pass = 0; pass < 2; pass++) {
+    fft_dit<32, -1>(v);
+    if (pass == 0) {
+#pragma unroll
+      for (int k1 = 1; k1 < 32; k1++) v[k1] = cmul(v[k1], tw[k1 * 32 + lane]);
+#pragma unroll
+      for (int k1 = 0; k1 < 32; k1++) tile[k1 * 32 + (lane ^ ((k1 & 15) << 1))] = v[k1];
+      __syncwarp();
+      const float4* row = reinterpret_cast<const float4*>(tile + lane * 32);
+      const int sw = lane & 15;
+      static_for<0, 16>([&](auto q) {
+        const float4 r = row[q ^ sw];
+        v[brev5(2 * q)] = make_float2(r.x, r.y);
+        v[brev5(2 * q + 1)] = make_float2(r.z, r.w);
+      });
+      __syncwarp();
+    }
+  }
+}
+
+struct SelShared {
+  float2 y[2][kL1K];
+  float2 g[1024];
+  float sqrtE[2][8];
+  unsigned short items[2 * kL1K];
+  unsigned short recheck[2 * kL1K];
+  int n_items, n_recheck;
+  unsigned char flag[2][kL1K];
+  float tail[512];
+  uint64_t bars[kSelWarps];
+};
+
+__device__ __forceinline__ float sqrt_approx(float x) {   // MUFU.SQRT; its ~2 ulp error sits far inside the gate's guard band
+  float r;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+
+// both frames of one logical bin from the packed half-scaled spectrum Z = FFT(0.5*w*(x_t + i x_{t+1}))
+__device__ __forceinline__ void unpack2(const float2* z, int l, float2& x0, float2& x1) {
+  const int j = (l == kL1K - 1) ? 511 : l;   // pseudo-bin: conj of bin N/2-1 (SURVEY B-4)
+  const float2 a = z[j], b = z[(1024 - j) & 1023];
+  x0 = make_float2(a.x + b.x, a.y - b.y);    // Z[j] + conj(Z[N-j])
+  x1 = make_float2(a.y + b.y, b.x - a.x);    // -i (Z[j] - conj(Z[N-j]))
+  if (l == kL1K - 1) { x0.y = -x0.y; x1.y = -x1.y; }
+}
+
+// Covariance of the P frames before `frame` from the ring (mvdr.cpp:87, :239-243) and its Cholesky factor.
+// ring_l: this bin's column of the per-stream ring [D][M][Lsel]; first = ring slot of frame-P.
+template <int MM, typename T>
+__device__ __forceinline__ void ring_cov_chol(const KernelParams& p, HermLower<MM, T>& A, T (&invd)[MM], const float2* ring_l, int first) {
+  typedef HermLower<MM, T> HL;
+  const int M = p.M, D = p.ring_depth;
+#pragma unroll
+  for (int i = 0; i < MM; i++) A.dg[i] = T(0);
+#pragma unroll
+  for (int i = 0; i < MM * (MM - 1) / 2; i++) A.lo[i] = mk<T>(T(0), T(0));
+  int slot = first;
+#pragma unroll 2
+  for (int k = 0; k < p.P; k++) {
+    const float2* src = ring_l + (size_t)slot * M * p.Lsel;   // [slot][mic][bin]: bin-fastest, coalesced across a warp
+    if (++slot == D) slot = 0;
+    cplx<T> h[MM];
+#pragma unroll
+    for (int i = 0; i < MM; i++) {
+      const float2 v = (i < M) ? src[(size_t)i * p.Lsel] : make_float2(0.f, 0.f);
+      h[i] = mk<T>((T)v.x, (T)v.y);
+    }
+#pragma unroll
+    for (int i = 0; i < MM; i++) {
+      A.dg[i] = fma_t<T>(h[i].x, h[i].x, fma_t<T>(h[i].y, h[i].y, A.dg[i]));
+#pragma unroll
+      for (int j = 0; j < i; j++) {   // h_i * conj(h_j)
+        cplx<T>& r = A.lo[HL::idx(i, j)];
+        r.x = fma_t<T>(h[i].x, h[j].x, fma_t<T>(h[i].y, h[j].y, r.x));
+        r.y = fma_t<T>(h[i].y, h[j].x, fma_t<T>(-h[i].x, h[j].y, r.y));
+      }
+    }
+  }
+  if (p.debug & 4) return;
+#pragma unroll
+  for (int j = 0; j < MM; j++) {
+    if (j < M) {
+      T d = A.dg[j] * T(1.001);   // whiteR diagonal (mvdr.cpp:242)
+#pragma unroll
+      for (int k = 0; k < j; k++) { const cplx<T> l = A.lo[HL::idx(j, k)]; d = fma_t<T>(-l.x, l.x, fma_t<T>(-l.y, l.y, d)); }
+      const T ljj = sqrt(d);
+      const T inv = T(1) / ljj;
+      A.dg[j] = ljj;
+      invd[j] = inv;
+#pragma unroll
+      for (int i = j + 1; i < MM; i++) {
+        if (i < M) {
+          cplx<T> acc = A.lo[HL::idx(i, j)];
+#pragma unroll
+          for (int k = 0; k < j; k++) {   // acc -= L[i][k] * conj(L[j][k])
+            const cplx<T> a = A.lo[HL::idx(i, k)], b = A.lo[HL::idx(j, k)];
+            acc.x = fma_t<T>(-a.x, b.x, fma_t<T>(-a.y, b.y, acc.x));
+            acc.y = fma_t<T>(-a.y, b.x, fma_t<T>(a.x, b.y, acc.y));
+          }
+          A.lo[HL::idx(i, j)] = mk<T>(acc.x * inv, acc.y * inv);
+        }
+      }
+    } else {
+      invd[j] = T(0);
+    }
+  }
+}
+
+// mvdr.cpp:86-94 with R = L L^H: z = L^{-1} d, u = L^{-1} x, y = (z^H u) / (z^H z)
+template <int MM, typename T>
+__device__ __forceinline__ float2 mvdr_ring_item(const KernelParams& p, const float2* ring_l, int first, const float2 (&x)[MM],
+                                                 const float2* steer_l) {
+  HermLower<MM, T> A;
+  T invd[MM];
+  ring_cov_chol<MM, T>(p, A, invd, ring_l, first);
+  if (p.debug & 8) return make_float2((float)A.dg[0], (float)A.lo[5].x);
+  cplx<T> z[MM], u[MM];
+#pragma unroll
+  for (int i = 0; i < MM; i++) {
+    const float2 d = (i < p.M) ? steer_l[i] : make_float2(0.f, 0.f);
+    z[i] = mk<T>((T)d.x, (T)d.y);
+    u[i] = mk<T>((T)x[i].x, (T)x[i].y);
+  }
+  fwd_solve<MM, T>(p, A, invd, z);
+  fwd_solve<MM, T>(p, A, invd, u);
+  const cplx<T> num = cdot_conj<MM, T>(z, u);
+  const T den = cdot_conj<MM, T>(z, z).x;
+  return make_float2((float)(num.x / den), (float)(num.y / den));
+}
+
+// lcmv.cpp:111-119: W = R^{-1} C (C^H R^{-1} C)^{-1}, y = W(:,0)^H x.  V = L^{-1} C, u = L^{-1} x, G = V^H V, b = V^H u,
+// y = g^H b with G g = e_0.
+template <int MM, typename T>
+__device__ __forceinline__ float2 lcmv_ring_item(const KernelParams& p, const float2* ring_l, int first, const float2 (&x)[MM],
+                                                 const float2* steer_l) {
+  HermLower<MM, T> A;
+  T invd[MM];
+  ring_cov_chol<MM, T>(p, A, invd, ring_l, first);
+  const int C = p.C, M = p.M;
+  cplx<T> u[MM];
+#pragma unroll
+  for (int i = 0; i < MM; i++) u[i] = mk<T>((T)x[i].x, (T)x[i].y);
+  fwd_solve<MM, T>(p, A, invd, u);
+  cplx<T> V[kMaxC][MM];
+  cplx<T> G[kMaxC][kMaxC];
+  cplx<T> b[kMaxC];
+  for (int c = 0; c < C; c++) {
+    cplx<T> v[MM];
+#pragma unroll
+    for (int i = 0; i < MM; i++) {
+      const float2 a = (i < M) ? steer_l[(size_t)c * M + i] : make_float2(0.f, 0.f);
+      v[i] = mk<T>((T)a.x, (T)a.y);
+    }
+    fwd_solve<MM, T>(p, A, invd, v);
+#pragma unroll
+    for (int i = 0; i < MM; i++) V[c][i] = v[i];
+    b[c] = cdot_conj<MM, T>(v, u);
+    for (int c2 = 0; c2 <= c; c2++) {
+      cplx<T> w[MM];
+#pragma unroll
+      for (int i = 0; i < MM; i++) w[i] = V[c2][i];
+      G[c][c2] = cdot_conj<MM, T>(v, w);
+    }
+  }
+  T gd[kMaxC];
+  for (int j = 0; j < C; j++) {
+    T d = G[j][j].x;
+    for (int k = 0; k < j; k++) d -= G[j][k].x * G[j][k].x + G[j][k].y * G[j][k].y;
+    const T ljj = sqrt(d);
+    gd[j] = T(1) / ljj;
+    for (int i = j + 1; i < C; i++) {
+      cplx<T> acc = G[i][j];
+      for (int k = 0; k < j; k++) {
+        const cplx<T> a = G[i][k], bb = G[j][k];
+        acc.x -= a.x * bb.x + a.y * bb.y;
+        acc.y -= a.y * bb.x - a.x * bb.y;
+      }
+      G[i][j] = mk<T>(acc.x * gd[j], acc.y * gd[j]);
+    }
+  }
+  cplx<T> q[kMaxC];
+  for (int i = 0; i < C; i++) {
+    cplx<T> acc = mk<T>(i == 0 ? T(1) : T(0), T(0));
+    for (int k = 0; k < i; k++) {
+      const cplx<T> l = G[i][k];
+      acc.x -= l.x * q[k].x - l.y * q[k].y;
+      acc.y -= l.x * q[k].y + l.y * q[k].x;
+    }
+    q[i] = mk<T>(acc.x * gd[i], acc.y * gd[i]);
+  }
+  cplx<T> g[kMaxC];
+  for (int i = C - 1; i >= 0; i--) {
+    cplx<T> acc = q[i];
+    for (int k = i + 1; k < C; k++) {
+      const cplx<T> l = G[k][i];
+      acc.x -= l.x * g[k].x + l.y * g[k].y;
+      acc.y -= l.x * g[k].y - l.y * g[k].x;
+    }
+    g[i] = mk<T>(acc.x * gd[i], acc.y * gd[i]);
+  }
+  cplx<T> y = mk<T>(T(0), T(0));
+  for (int c = 0; c < C; c++) {
+    y.x += g[c].x * b[c].x + g[c].y * b[c].y;
+    y.y += g[c].x * b[c].y - g[c].y * b[c].x;
+  }
+  return make_float2((float)y.x, (float)y.y);
+}
+
+template <int ALGO>
+__global__ void __launch_bounds__(kSelThreads, ALGO == ALGO_LCMV ? 1 : 2) sel_pairs_kernel(const KernelParams p, const int use_tma) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  float2* tw = reinterpret_cast<float2*>(smem_raw);             // [32][32]
+  float2* ztiles = tw + 1024;                                     // [8][1024] exchange tile, then Z linear
+  SelShared& sc = *reinterpret_cast<SelShared*>(ztiles + kSelWarps * 1024);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int M = p.M, D = p.ring_depth;
+  constexpr int H = 512;
+  const int s = blockIdx.x + p.stream_begin;
+
+  for (int i = tid; i < 1024; i += kSelThreads) {
+    const int k1 = i >> 5, l = i & 31;
+    float sn, cs;
+    sincospif(-2.0f * (float)((k1 * l) & 1023) / 1024.0f, &sn, &cs);
+    tw[i] = make_float2(cs, sn);
+  }
+  for (int i = tid; i < H; i += kSelThreads) sc.tail[i] = p.tail[(size_t)s * H + i];
+  if (lane == 0) mbar_init(&sc.bars[warp], 1);
+  mbar_fence_init();
+  __syncthreads();
+
+  double sd, cd;
+  sincospi((double)lane / 1024.0, &sd, &cd);
+  const float s_l = (float)(0.5 * sd), c_l = (float)(0.5 * cd);                 // analysis window * 0.5
+  const float s_o = (float)(sd * p.out_scale), c_o = (float)(cd * p.out_scale); // synthesis window * out_amp / N
+
+  float2* myz = ztiles + (size_t)warp * 1024;
+  float* mystage = reinterpret_cast<float*>(myz);   // hops t-1..t+1 land in the tile before it holds Z
+  const float* in_s = p.in + (size_t)s * p.in_stream_stride + (size_t)warp * p.in_mic_stride;
+  const int nh = p.hop_end - p.hop_begin;
+  const int npairs = (nh + 1) >> 1;
+
+  // hops t-1..t+1 of microphone `warp` -> staging (TMA), hop -1 = per-stream state (util.h:275-277)
+  auto issue = [&](int t) {
+    if (lane != 0 || warp >= M) return;
+    const bool two = t + 1 < p.hop_end;
+    const uint32_t nb = (two ? 2u : 1u) * H * 4u;
+    mbar_expect_tx(&sc.bars[warp], nb + H * 4u);
+    const float* prev = (t - 1 < 0) ? p.prev_hop + ((size_t)s * M + warp) * H : in_s + (size_t)(t - 1) * H;
+    bulk_g2s(mystage, prev, H * 4u, &sc.bars[warp]);
+    bulk_g2s(mystage + H, in_s + (size_t)t * H, nb, &sc.bars[warp]);
+  };
+  if (use_tma && npairs > 0) issue(p.hop_begin);
+
+  for (int ip = 0; ip <= npairs; ip++) {
+    const int t = p.hop_begin + 2 * ip;
+    const bool live = ip < npairs;
+    const bool two = t + 1 < p.hop_end;
+    const int nf = two ? 2 : 1;
+    // ------------------------------------------------------------------ A: forward transforms
+    if (live && warp < M) {
+      float2 v[32];
+      if (use_tma) {
+        mbar_wait(&sc.bars[warp], ip & 1);
+      } else {   // unaligned caller buffers: plain warp copy, no prefetch
+        const float* prev = (t - 1 < 0) ? p.prev_hop + ((size_t)s * M + warp) * H : in_s + (size_t)(t - 1) * H;
+        for (int i = lane; i < H; i += 32) {
+          mystage[i] = prev[i];
+          mystage[H + i] = in_s[(size_t)t * H + i];
+          mystage[2 * H + i] = two ? in_s[(size_t)(t + 1) * H + i] : 0.f;
+        }
+        __syncwarp();
+      }
+      static_for<0, 16>([&](auto r) {
+        const float a = mystage[32 * r + lane], bb = mystage[512 + 32 * r + lane];
+        const float c = two ? mystage[1024 + 32 * r + lane] : 0.0f;
+        const float w0 = win1024<r>(s_l, c_l);
+        const float w1 = win1024<r + 16>(s_l, c_l);
+        v[brev5(r)] = make_float2(a * w0, bb * w0);
+        v[brev5(r + 16)] = make_float2(bb * w1, c * w1);
+      });
+      __syncwarp();   // staged samples consumed: the tile becomes the exchange buffer, then Z
+      {   // sqrt of the windowed frame energies: scale of the FP32 FFT's absolute error (gate guard band)
+        float e0 = 0.f, e1 = 0.f;
+#pragma unroll
+        for (int r = 0; r < 32; r++) { e0 = fmaf(v[r].x, v[r].x, e0); e1 = fmaf(v[r].y, v[r].y, e1); }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { e0 += __shfl_xor_sync(0xffffffffu, e0, o); e1 += __shfl_xor_sync(0xffffffffu, e1, o); }
+        if (lane == 0) { sc.sqrtE[0][warp] = 2.0f * sqrtf(e0); sc.sqrtE[1][warp] = 2.0f * sqrtf(e1); }
+      }
+      sel_fft1024_fwd(v, myz, tw, lane);
+#pragma unroll
+      for (int k2 = 0; k2 < 32; k2++) myz[k2 * 32 + lane] = v[k2];
+    }
+    if (tid == 0) { sc.n_items = 0; sc.n_recheck = 0; }
+    __syncthreads();   // (a) Z complete; G of the previous pair complete
+    const int fr0 = (p.ring_slot0 + (t - p.hop_begin)) % D;   // ring slot of frame t
+    // ------------------------------------------------------------------ B1: gate, history append, defaults
+    if (live) {
+      for (int l = tid; l < kL1K; l += kSelThreads) {
+        const bool inb = p.inband[l] != 0 && !(ALGO == ALGO_MVDR && l == 0);
+        float2 x0[8], x1[8];
+        float st0 = 0.f, st1 = 0.f;
+        if (!inb) {   // out of band: output 0 (mvdr.cpp:103), except mvdr's bin 0 which passes microphone 0 through
+          float2 a = make_float2(0.f, 0.f), b = a;
+          if (ALGO == ALGO_MVDR && l == 0) unpack2(ztiles, 0, a, b);
+          sc.flag[0][l] = 0; sc.flag[1][l] = 0;
+          sc.y[0][l] = a; sc.y[1][l] = b;
+          continue;
+        }
+#pragma unroll
+        for (int ch = 0; ch < 8; ch++) {
+          if (ch < M) {
+            unpack2(ztiles + ch * 1024, l, x0[ch], x1[ch]);
+            st0 += sqrt_approx(fmaf(x0[ch].x, x0[ch].x, x0[ch].y * x0[ch].y));
+            st1 += sqrt_approx(fmaf(x1[ch].x, x1[ch].x, x1[ch].y * x1[ch].y));
+          } else {
+            x0[ch] = x1[ch] = make_float2(0.f, 0.f);
+          }
+        }
+        float2 y0 = make_float2(0.f, 0.f), y1 = y0;
+        unsigned char f0 = 0, f1 = 0;
+        {
+          float es0 = 0.f, es1 = 0.f;
+          for (int ch = 0; ch < M; ch++) { es0 += sc.sqrtE[0][ch]; es1 += sc.sqrtE[1][ch]; }
+          const float g0 = 2.0e-5f * es0 + 1.0e-6f * p.thr_mag, g1 = 2.0e-5f * es1 + 1.0e-6f * p.thr_mag;
+          if (fabsf(st0 - p.thr_mag) <= g0) sc.recheck[atomicAdd(&sc.n_recheck, 1)] = (unsigned short)(l * 2);
+          else if (st0 > p.thr_mag) f0 = 1;
+          if (two) {
+            if (fabsf(st1 - p.thr_mag) <= g1) sc.recheck[atomicAdd(&sc.n_recheck, 1)] = (unsigned short)(l * 2 + 1);
+            else if (st1 > p.thr_mag) f1 = 1;
+          }
+          y0 = make_float2(0.01f * x0[0].x, 0.01f * x0[0].y);   // mvdr.cpp:96 (overwritten when selected)
+          y1 = make_float2(0.01f * x1[0].x, 0.01f * x1[0].y);
+          if (ALGO != ALGO_GSS && !(p.debug & 2)) {   // mvdr.cpp:99-101: every in-band bin appends every frame
+            float2* ring_l = p.hist + (size_t)s * D * M * p.Lsel + p.sel_slot[l];
+            int fs = fr0;
+#pragma unroll
+            for (int f = 0; f < 2; f++) {
+              if (f < nf) {
+                float2* dst = ring_l + (size_t)fs * M * p.Lsel;
+#pragma unroll
+                for (int i = 0; i < 8; i++)
+                  if (i < M) dst[(size_t)i * p.Lsel] = f ? x1[i] : x0[i];
+              }
+              if (++fs == D) fs = 0;
+            }
+          }
+        }
+        sc.flag[0][l] = f0; sc.flag[1][l] = two ? f1 : 0;
+        sc.y[0][l] = y0; sc.y[1][l] = y1;
+      }
+    }
+    __syncthreads();   // (b)
+    // ------------------------------------------------------------------ B1b: FP64 re-decision of guarded bins
+    if (live && sc.n_recheck > 0) {
+      for (int q = warp; q < sc.n_recheck; q += kSelWarps) {
+        const int l = sc.recheck[q] >> 1, f = sc.recheck[q] & 1;
+        const bool sel = gate_fp64(p, s, t, l, f, lane);
+        if (lane == 0 && sel) sc.flag[f][l] = 1;
+      }
+    }
+    __syncthreads();
+    // work list: runs of consecutive bins stay contiguous, so neighbouring threads of B2 read neighbouring
+    // ring addresses.  mvdr/lcmv: one item per selected (bin, frame); gss: one per bin (its recursion is
+    // sequential over the frames of a bin).
+    if (live) {
+      for (int f = 0; f < (ALGO == ALGO_GSS ? 1 : nf); f++)
+        for (int base = warp * 32; base < kL1K; base += kSelThreads) {
+          const int l = base + lane;
+          bool on = false;
+          if (l < kL1K) on = (ALGO == ALGO_GSS) ? ((sc.flag[0][l] | sc.flag[1][l]) != 0) : (sc.flag[f][l] != 0);
+          const unsigned m = __ballot_sync(0xffffffffu, on);
+          int pos = 0;
+          if (lane == 0 && m) pos = atomicAdd(&sc.n_items, __popc(m));
+          pos = __shfl_sync(0xffffffffu, pos, 0);
+          if (on) sc.items[pos + __popc(m & ((1u << lane) - 1u))] = (unsigned short)(l * 2 + f);
+        }
+    }
+    __syncthreads();   // (c) work list complete
+    // ------------------------------------------------------------------ inverse of the PREVIOUS pair (last warp)
+    if (warp == kSelWarps - 1 && ip > 0) {
+      const int tp = t - 2;
+      const bool ptwo = tp + 1 < p.hop_end;
+      float2 v[32];
+      static_for<0, 32>([&](auto n1) { const float2 gg = sc.g[n1 * 32 + lane]; v[brev5(n1)] = make_float2(gg.y, gg.x); });
+      __syncwarp();
+      sel_fft1024_fwd(v, sc.g, tw, lane);   // IFFT(G) = swap(FFT(swap(G))); G itself is the exchange tile
+      float* o0 = p.out + (size_t)s * p.out_stream_stride + (size_t)tp * H;
+      static_for<0, 16>([&](auto m2) {
+        const float w0 = win1024<m2>(s_o, c_o);
+        const float w1 = win1024<m2 + 16>(s_o, c_o);
+        const float y0a = v[m2].y * w0, y0b = v[m2 + 16].y * w1;   // frame t: first / second half
+        const float y1a = v[m2].x * w0, y1b = v[m2 + 16].x * w1;   // frame t+1
+        o0[32 * m2 + lane] = sc.tail[32 * m2 + lane] + y0a;        // util.h:301-302
+        if (ptwo) o0[H + 32 * m2 + lane] = y0b + y1a;
+        sc.tail[32 * m2 + lane] = ptwo ? y1b : y0b;
+      });
+    }
+    // ------------------------------------------------------------------ B2: per-item solves
+    if (live) {
+      // items start on warp 0; the last warp (busy with the inverse) is reached only by large work lists
+      for (int q = tid; q < ((p.debug & 1) ? 0 : sc.n_items); q += kSelThreads) {
+        const int l = sc.items[q] >> 1, f = sc.items[q] & 1;
+        const int slot = p.sel_slot[l];
+        const float2* steer_l = p.steer + (size_t)l * p.C * M;
+        if (ALGO == ALGO_GSS) {
+          float2* Wg = p.gss_w + (size_t)s * 8 * M * p.Lsel + slot;   // [B][8][M][Lsel]
+          for (int ff = 0; ff < nf; ff++) {
+            if (!sc.flag[ff][l]) continue;
+            float2 x[8];
+#pragma unroll
+            for (int ch = 0; ch < 8; ch++) {
+              float2 a, b;
+              if (ch < M) unpack2(ztiles + ch * 1024, l, a, b); else a = b = make_float2(0.f, 0.f);
+              x[ch] = ff ? b : a;
+            }
+            sc.y[ff][l] = gss_item(p, Wg, (size_t)p.Lsel, x, steer_l);
+          }
+        } else {
+          float2 x[8];
+#pragma unroll
+          for (int ch = 0; ch < 8; ch++) {
+            float2 a, b;
+            if (ch < M) unpack2(ztiles + ch * 1024, l, a, b); else a = b = make_float2(0.f, 0.f);
+            x[ch] = f ? b : a;
+          }
+          const float2* ring_l = p.hist + (size_t)s * D * M * p.Lsel + slot;
+          int first = fr0 + f - p.P;   // slot of frame (t+f) - P
+          first %= D; if (first < 0) first += D;
+          sc.y[f][l] = (ALGO == ALGO_MVDR) ? mvdr_ring_item<8, float>(p, ring_l, first, x, steer_l)
+                                           : lcmv_ring_item<8, double>(p, ring_l, first, x, steer_l);
+        }
+      }
+    }
+    __syncthreads();   // (e) Y complete; G consumed by the inverse; Z no longer needed
+    if (use_tma && ip + 1 < npairs) {   // the spectrum tiles are free: stage the next pair's hops into them
+      fence_proxy_async();
+      issue(t + 2);
+    }
+    // ------------------------------------------------------------------ B3: Hermitian assembly, diagnostics
+    if (live) {
+      for (int l = tid; l < kL1K; l += kSelThreads) {
+        if (l <= 512) {
+          float2 y0 = sc.y[0][l], y1 = two ? sc.y[1][l] : make_float2(0.f, 0.f);
+          if (l == 511) {   // Hermitian part of the asymmetric pair (N/2-1, N/2+1): Yh = (Y[N/2-1] + conj(Y[N/2+1])) / 2
+            const float2 p0 = sc.y[0][kL1K - 1], p1 = two ? sc.y[1][kL1K - 1] : make_float2(0.f, 0.f);
+            y0 = make_float2(0.5f * (y0.x + p0.x), 0.5f * (y0.y - p0.y));
+            y1 = make_float2(0.5f * (y1.x + p1.x), 0.5f * (y1.y - p1.y));
+          }
+          if (l == 0 || l == 512) { y0.y = 0.f; y1.y = 0.f; }   // Re(): self-conjugate bins
+          sc.g[l] = make_float2(y0.x - y1.y, y0.y + y1.x);                          // Yh_t + i Yh_{t+1}
+          if (l > 0 && l < 512) sc.g[1024 - l] = make_float2(y0.x + y1.y, y1.x - y0.y);   // conj(Yh_t) + i conj(Yh_{t+1})
+        }
+        if (p.capture) {
+          for (int f = 0; f < nf; f++) {
+            unsigned char* cap = p.capture + (size_t)s * p.capture_stream_stride + (size_t)(t + f) * p.N;
+            const unsigned char fl = sc.flag[f][l];
+            if (l <= 512) {
+              cap[l] = fl;
+              if (l > 0 && l < 511) cap[1024 - l] = fl;
+            } else {
+              cap[513] = fl;
+            }
+          }
+        }
+      }
+    }
+  }
+  __syncthreads();
+  for (int i = tid; i < H; i += kSelThreads) p.tail[(size_t)s * H + i] = sc.tail[i];
+}
+
+size_t sel_pairs_smem() { return sizeof(float2) * (1024 + kSelWarps * 1024) + sizeof(SelShared) + 128; }
+
+bool sel_pairs_supported(const KernelParams& p, int algo) {
+  return p.H == 512 && p.M <= 8 && (algo == ALGO_MVDR || algo == ALGO_LCMV || algo == ALGO_GSS) && p.C <= kMaxC;
+}
+
+cudaError_t launch_sel_pairs(int algo, const KernelParams& p, cudaStream_t st) {
+  const int use_tma = ((reinterpret_cast<uintptr_t>(p.in) & 15) == 0 && (p.in_stream_stride & 3) == 0 && (p.in_mic_stride & 3) == 0) ? 1 : 0;
+  const size_t smem = sel_pairs_smem();
+  void (*k)(KernelParams, int) = nullptr;
+  switch (algo) {
+    case ALGO_MVDR: k = sel_pairs_kernel<ALGO_MVDR>; break;
+    case ALGO_LCMV: k = sel_pairs_kernel<ALGO_LCMV>; break;
+    case ALGO_GSS: k = sel_pairs_kernel<ALGO_GSS>; break;
+    default: return cudaErrorNotSupported;
+  }
+  cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  k<<<p.n_streams, kSelThreads, smem, st>>>(p, use_tma);
+  return cudaGetLastError();
+}
+
+}   // namespace bf
