@@ -51,6 +51,8 @@ struct KernelParams {
   float gss_dj2_scale;      // 2 * (1/(K+1)) in integer arithmetic (gss.cpp:133) -> 2 for K=0 else 0
   float min_phase_rad, mag_mult, thr_phase_mag;   // phase
   float min_mag;            // phasempf
+  const float* win_f;       // [N] sqrt-hann (float), frame-size-generic kernel
+  const float2* twid_f;     // [N] e^{-2 pi i k/N} (float), frame-size-generic kernel
   const double* win_d;      // [N] sqrt-hann in double, for FP64 rechecks
   const double2* twid_d;    // [N] e^{-2 pi i k/N} in double, for FP64 rechecks
   const double2* steer_d;   // [L][M] look-direction steering in double (phase family rechecks)

@@ -30,6 +30,8 @@ bool das_pairs_supported(const KernelParams& p);
 cudaError_t launch_das_pairs(const KernelParams& p, cudaStream_t st, int sm_count);
 bool sel_pairs_supported(const KernelParams& p, int algo);
 cudaError_t launch_sel_pairs(int algo, const KernelParams& p, cudaStream_t st);
+cudaError_t launch_frames_kernel_n(int algo, const KernelParams& p, cudaStream_t st);
+size_t frames_kernel_n_smem(int N, int M);
 }   // namespace bf
 
 typedef std::complex<double> cd;
@@ -84,6 +86,8 @@ struct bf_handle {
   int Lsel = 0;
   float2* d_hist = nullptr;     // mvdr/lcmv: [B][Lsel][P+2][M]
   float2* d_gss_w = nullptr;    // gss: [B][Lsel][C][M]
+  float* d_win_f = nullptr;
+  float2* d_twid_f = nullptr;
   double* d_win_d = nullptr;
   double2* d_twid_d = nullptr;
   double2* d_steer_d = nullptr;   // phase family: [L][M] look-direction steering in double
@@ -344,7 +348,14 @@ extern "C" int bf_create(bf_handle** out, const bf_config* cfg, uint32_t n_strea
   *out = nullptr;
   if (cfg->n_mics < 1 || cfg->n_mics > BF_MAX_MICS) return fail(BF_ERR_INVALID, "bf_create: n_mics must be in [1, 64]");
   if (n_streams < 1) return fail(BF_ERR_INVALID, "bf_create: n_streams must be >= 1");
-  if (cfg->hop != 512) return fail(BF_ERR_INVALID, "bf_create: this build supports hop 512 (1024-point frames) only");
+  if (cfg->hop != 256 && cfg->hop != 512 && cfg->hop != 1024 && cfg->hop != 2048)
+    return fail(BF_ERR_INVALID, "bf_create: hop (JACK period) must be 256, 512, 1024 or 2048 (512- to 4096-point frames)");
+  if (cfg->hop != 512) {
+    if (cfg->algo == BF_ALGO_MVDR || cfg->algo == BF_ALGO_LCMV || cfg->algo == BF_ALGO_GSS)
+      return fail(BF_ERR_INVALID, "bf_create: mvdr/lcmv/gss are built for 1024-point frames (hop 512) only");
+    if (bf::frames_kernel_n_smem(2 * (int)cfg->hop, cfg->n_mics) > 232448)
+      return fail(BF_ERR_INVALID, "bf_create: too many microphones for this frame size (spectra must fit 227 KB of shared memory)");
+  }
   if (cfg->algo < 0 || cfg->algo > 5) return fail(BF_ERR_INVALID, "bf_create: unknown algo");
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1 || cfg->device >= ndev)
@@ -443,6 +454,22 @@ extern "C" int bf_create(bf_handle** out, const bf_config* cfg, uint32_t n_strea
       cudaMemcpy(h->d_twid_d, twd.data(), sizeof(double2) * h->N, cudaMemcpyHostToDevice);
     }
   }
+  {
+    // float window / twiddle tables of the frame-size-generic kernel (util.h:201-211)
+    std::vector<float> wf(h->N);
+    std::vector<float2> tf(h->N);
+    for (uint32_t n = 0; n < h->N; n++) {
+      wf[n] = (float)std::sqrt(0.5 - 0.5 * std::cos(2 * kPi * n / (h->N)));
+      const double ang = -2.0 * kPi * (double)n / (double)h->N;
+      tf[n] = make_float2((float)std::cos(ang), (float)std::sin(ang));
+    }
+    if (cudaMalloc(&h->d_win_f, sizeof(float) * h->N) != cudaSuccess || cudaMalloc(&h->d_twid_f, sizeof(float2) * h->N) != cudaSuccess) {
+      bf_destroy(h);
+      return fail(BF_ERR_ALLOC, "bf_create: device allocation failed (tables)");
+    }
+    cudaMemcpy(h->d_win_f, wf.data(), sizeof(float) * h->N, cudaMemcpyHostToDevice);
+    cudaMemcpy(h->d_twid_f, tf.data(), sizeof(float2) * h->N, cudaMemcpyHostToDevice);
+  }
   cudaMemset(h->d_prev_hop, 0, sizeof(float) * prev_n);   // util.h:275-277: one hop of zeros pre-loaded
   cudaMemset(h->d_tail, 0, sizeof(float) * tail_n);       // util.h:285: calloc'ed out_buff
   int rc = upload_tables(h, h->own_stream);
@@ -461,7 +488,7 @@ extern "C" void bf_destroy(bf_handle* h) {
   if (h->st_d2h) cudaStreamDestroy(h->st_d2h);
   for (int i = 0; i < 8; i++) { if (h->ev_in[i]) cudaEventDestroy(h->ev_in[i]); if (h->ev_k[i]) cudaEventDestroy(h->ev_k[i]); }
   cudaFree(h->d_steer_d); cudaFree(h->d_mpf_state); cudaFree(h->d_smooth_hist);
-  cudaFree(h->d_sel_slot); cudaFree(h->d_sel_list); cudaFree(h->d_hist); cudaFree(h->d_gss_w); cudaFree(h->d_win_d); cudaFree(h->d_twid_d);
+  cudaFree(h->d_sel_slot); cudaFree(h->d_sel_list); cudaFree(h->d_hist); cudaFree(h->d_gss_w); cudaFree(h->d_win_d); cudaFree(h->d_twid_d); cudaFree(h->d_win_f); cudaFree(h->d_twid_f);
   if (h->h_stage_in) cudaFreeHost(h->h_stage_in);
   if (h->h_stage_out) cudaFreeHost(h->h_stage_out);
   delete h;
@@ -589,6 +616,7 @@ static int run_segment(bf_handle* h, const float* in, size_t ss, size_t ms, floa
   p.lambda_mu = (float)(1 - h->cfg.lambda * h->cfg.mu);
   p.gss_w = h->d_gss_w;
   p.gss_dj2_scale = (float)(2 * (1 / (size_t)h->C));   // gss.cpp:133: integer arithmetic (SURVEY B-7)
+  p.win_f = h->d_win_f; p.twid_f = h->d_twid_f;
   p.win_d = h->d_win_d; p.twid_d = h->d_twid_d; p.steer_d = h->d_steer_d;
   p.mag_threshold_d = h->cfg.mag_threshold;
   p.min_phase_rad_d = h->cfg.min_phase * M_PI / 180;   // phase.cpp:175
@@ -617,7 +645,10 @@ static int run_segment(bf_handle* h, const float* in, size_t ss, size_t ms, floa
     CUDA_TRY(cudaEventCreate(&ev1));
     CUDA_TRY(cudaEventRecord(ev0, st));
   }
-  if (h->cfg.algo == BF_ALGO_DAS && bf::das_pairs_supported(p)) CUDA_TRY(bf::launch_das_pairs(p, st, h->sm_count));
+  static const bool force_generic = getenv("BF_GENERIC") != nullptr;   // debug: cross-check the generic kernel at N = 1024
+  const bool gen_algo = h->cfg.algo == BF_ALGO_DAS || h->cfg.algo == BF_ALGO_PHASE || h->cfg.algo == BF_ALGO_PHASEMPF;
+  if (h->N != 1024 || (force_generic && gen_algo)) CUDA_TRY(bf::launch_frames_kernel_n(h->cfg.algo, p, st));
+  else if (h->cfg.algo == BF_ALGO_DAS && bf::das_pairs_supported(p)) CUDA_TRY(bf::launch_das_pairs(p, st, h->sm_count));
   else if (bf::sel_pairs_supported(p, h->cfg.algo)) CUDA_TRY(bf::launch_sel_pairs(h->cfg.algo, p, st));
   else CUDA_TRY(bf::launch_frames_kernel_1024(h->cfg.algo, p, st));
   if (h->profiling) {

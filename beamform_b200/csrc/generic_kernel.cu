@@ -1,0 +1,464 @@
+// Frame-size-generic fused kernel (512-, 2048- and 4096-point frames; das / phase / phasempf), sm_100a.
+//
+//   reference path replaced (citations /root/reference/beamform/src/): util.h:217-253,289-314 (window, framing,
+//   OLA), das.cpp:47-70, phase.cpp:70-134, phasempf.cpp:140-302 + the output smoother phasempf.cpp:78-83,331-334.
+//
+// One CTA owns one stream and walks its frame pairs in order.  The transform is a shared-memory Stockham FFT whose
+// radix-8/16 butterflies run in registers (fft_reg.cuh): each pass lets every thread gather R points of one
+// transform, multiply by the pass twiddles, run an R-point register FFT and scatter the results in place (all
+// reads of a round precede all writes: two block barriers per round).  4096 = 16*16*16, 2048 = 16*16*8,
+// 1024 = 16*8*8, 512 = 8*8*8.  As in the 1024-point kernels the two real frames of a pair ride in the real and
+// imaginary parts of one complex transform, spectra never leave shared memory and every input sample is
+// fetched from HBM once (its second touch hits L1/L2).
+//
+// The 1024-point frames of the headline configurations use the register-resident warp FFT kernels
+// (das_kernel.cu, sel_kernel.cu, frames_kernel.cu); this kernel covers the other frame sizes, notably the
+// 4096-point PhaseMPF configuration C4.
+#include "bf_device.h"
+#include "fft_reg.cuh"
+
+namespace bf {
+
+constexpr int kGenThreads = 256;
+
+template <int NN>
+struct GenScratch {
+  static constexpr int L = NN / 2 + 2;
+  float2 y[2][L];
+  float sqrtE[2][BF_MAX_MICS_DEV];
+  float esum[2][BF_MAX_MICS_DEV];
+  unsigned short recheck[2 * L];
+  int n_recheck;
+  unsigned char flag[2][L];   // bit0: magnitude gate passed (phase.cpp:99), bit1: bin kept as source of interest
+  float tail[NN / 2];
+  float ola[64 + NN];         // phasempf: post-OLA moving-average window (smooth_size <= 64)
+};
+
+// One Stockham pass of radix R over `nfft` transforms of size NN stored back to back in z (in place).
+//   j in [0, NN/R): k = j mod Ns; v[q] = z[j + q*NN/R] * W_{Ns*R}^{k q}; V = DFT_R(v); z[(j/Ns)*Ns*R + k + q*Ns] = V[q]
+template <int NN, int R, int DIR>
+__device__ __forceinline__ void stockham_pass(float2* z, int nfft, int Ns, const float2* __restrict__ tw, int tid) {
+  constexpr int per = NN / R;                                  // tasks per transform
+  constexpr int g = kGenThreads / per > 0 ? kGenThreads / per : 1;   // transforms per round
+  static_assert(per <= kGenThreads, "one round must cover a whole transform");
+  const int f_local = tid / per, j = tid - f_local * per;
+  const int k = j & (Ns - 1);
+  const int tstep = k * (NN / (Ns * R));                      // twiddle index step: W_NN^{tstep*q}
+  const int j0 = (j / Ns) * Ns * R + k;
+  for (int f0 = 0; f0 < nfft; f0 += g) {
+    const int f = f0 + f_local;
+    const bool on = f_local < g && f < nfft;
+    float2 v[R];
+    float2* zz = z + (size_t)f * NN;
+    if (on) {
+#pragma unroll
+      for (int q = 0; q < R; q++) {
+        float2 a = zz[j + q * per];
+        if (q > 0) {
+          const float2 w = __ldg(tw + ((tstep * q) & (NN - 1)));
+          a = (DIR < 0) ? cmul(a, w) : cmulc(a, w);
+        }
+        v[brev(q, ilog2(R))] = a;
+      }
+      fft_dit<R, DIR>(v);
+    }
+    __syncthreads();   // every read of this round precedes every write
+    if (on) {
+#pragma unroll
+      for (int q = 0; q < R; q++) zz[j0 + q * Ns] = v[q];
+    }
+    __syncthreads();
+  }
+}
+
+template <int NN, int DIR>
+__device__ __forceinline__ void block_fft(float2* z, int nfft, const float2* __restrict__ tw, int tid) {
+  if constexpr (NN == 4096) {
+    stockham_pass<NN, 16, DIR>(z, nfft, 1, tw, tid);
+    stockham_pass<NN, 16, DIR>(z, nfft, 16, tw, tid);
+    stockham_pass<NN, 16, DIR>(z, nfft, 256, tw, tid);
+  } else if constexpr (NN == 2048) {
+    stockham_pass<NN, 16, DIR>(z, nfft, 1, tw, tid);
+    stockham_pass<NN, 16, DIR>(z, nfft, 16, tw, tid);
+    stockham_pass<NN, 8, DIR>(z, nfft, 256, tw, tid);
+  } else if constexpr (NN == 1024) {
+    stockham_pass<NN, 16, DIR>(z, nfft, 1, tw, tid);
+    stockham_pass<NN, 8, DIR>(z, nfft, 16, tw, tid);
+    stockham_pass<NN, 8, DIR>(z, nfft, 128, tw, tid);
+  } else {
+    static_assert(NN == 512, "supported frame sizes: 512, 1024, 2048, 4096");
+    stockham_pass<NN, 8, DIR>(z, nfft, 1, tw, tid);
+    stockham_pass<NN, 8, DIR>(z, nfft, 8, tw, tid);
+    stockham_pass<NN, 8, DIR>(z, nfft, 64, tw, tid);
+  }
+}
+
+// X_i[j] of frame f (0: t, 1: t+1) from the packed half-scaled spectrum Z = FFT(0.5*w*(x_t + i x_{t+1}))
+template <int NN>
+__device__ __forceinline__ float2 unpack_n(const float2* z, int l, int f) {
+  constexpr int L = NN / 2 + 2;
+  const int j = (l == L - 1) ? NN / 2 - 1 : l;   // pseudo-bin: conj of bin N/2-1 (SURVEY B-4)
+  const float2 a = z[j], b = z[(NN - j) & (NN - 1)];
+  float2 x;
+  if (f == 0) x = make_float2(a.x + b.x, a.y - b.y);
+  else x = make_float2(a.y + b.y, b.x - a.x);
+  if (l == L - 1) x.y = -x.y;
+  return x;
+}
+
+__device__ __forceinline__ float wrap_diff_n(float a, float b) {   // phase.cpp:58-60
+  const float d = fabsf(a - b);
+  return d > 3.14159265358979f ? 6.28318530717959f - d : d;
+}
+
+// FP64 re-decision of one (bin, frame): exact double DFT of that bin for every microphone, one warp per item
+template <int NN>
+__device__ __forceinline__ unsigned phase_decide_fp64_n(const KernelParams& p, int s, int t, int l, int f, int lane, bool use_gate) {
+  constexpr int L = NN / 2 + 2, H = NN / 2;
+  const int j = (l == L - 1) ? NN / 2 + 1 : l;
+  double phi[BF_MAX_MICS_DEV];
+  double magsum = 0.0;
+  for (int ch = 0; ch < p.M; ch++) {
+    const int hf = t + f;
+    const float* h0 = (hf - 1 < 0) ? p.prev_hop + ((size_t)s * p.M + ch) * H
+                                   : p.in + (size_t)s * p.in_stream_stride + (size_t)ch * p.in_mic_stride + (size_t)(hf - 1) * H;
+    const float* h1 = p.in + (size_t)s * p.in_stream_stride + (size_t)ch * p.in_mic_stride + (size_t)hf * H;
+    double re = 0.0, im = 0.0;
+    for (int n = lane; n < NN; n += 32) {
+      const double xv = (double)(n < H ? h0[n] : h1[n - H]) * p.win_d[n];
+      const double2 w = p.twid_d[(int)(((long long)j * n) & (NN - 1))];
+      re = fma(xv, w.x, re);
+      im = fma(xv, w.y, im);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      re += __shfl_xor_sync(0xffffffffu, re, o);
+      im += __shfl_xor_sync(0xffffffffu, im, o);
+    }
+    magsum += hypot(re, im);
+    const double2 w = p.steer_d[(size_t)l * p.M + ch];
+    phi[ch] = atan2(im * w.x - re * w.y, re * w.x + im * w.y);
+  }
+  unsigned fl = 0;
+  if (!use_gate || (magsum / p.M) / (double)NN > p.mag_threshold_d) fl |= 1;
+  double tot = 0.0;   // phase.cpp:53-68: association order of the recursion
+  int num = 0;
+  for (int a = p.M - 2; a >= 0; a--) {
+    double lvl = 0.0;
+    for (int b = a + 1; b < p.M; b++) {
+      double d = fabs(phi[a] - phi[b]);
+      if (d > 3.14159265358979323846) d = 2 * 3.14159265358979323846 - d;
+      lvl += d;
+      num++;
+    }
+    tot = lvl + tot;
+  }
+  if (tot / (double)num < p.min_phase_rad_d) fl |= 2;
+  return fl;
+}
+
+// phase.cpp:70-134 / phasempf.cpp:193-302 for the two frames of a pair -> sc.y
+template <int ALGO, int NN>
+__device__ __forceinline__ void phase_pair_n(const KernelParams& p, int s, int t, bool two, const float2* zall, GenScratch<NN>& sc,
+                                             int& cur_L, int& first_L, int tid) {
+  constexpr int L = NN / 2 + 2;
+  const int M = p.M, nf = two ? 2 : 1;
+  const int lane = tid & 31, warp = tid >> 5;
+  constexpr bool kGate = (ALGO == ALGO_PHASE);
+  const int npairs = M * (M - 1) / 2;
+  // ---- decisions (FP32, guard band -> FP64 recheck list) ----
+  for (int l = tid; l < L; l += kGenThreads) {
+    for (int f = 0; f < nf; f++) {
+      if (l == 0) { sc.flag[f][l] = 0; continue; }
+      float magsum = 0.f, guard = 0.f, esum = 0.f;
+      float phi[BF_MAX_MICS_DEV];
+      const float2* st = p.steer + (size_t)l * p.C * M;
+      for (int ch = 0; ch < M; ch++) {
+        const float2 x = unpack_n<NN>(zall + (size_t)ch * NN, l, f);
+        const float2 w = st[ch];
+        const float a = sqrtf(fmaf(x.x, x.x, x.y * x.y));
+        magsum += a;
+        phi[ch] = atan2f(x.y * w.x - x.x * w.y, x.x * w.x + x.y * w.y);   // arg(conj(w) x)
+        const float e = sc.sqrtE[f][ch];
+        esum += e;
+        guard += fminf(3.2f, 4.0e-6f * e / fmaxf(a, 1e-30f) + 2.0e-6f);
+      }
+      float tot = 0.f;
+      for (int a = M - 2; a >= 0; a--) {
+        float lvl = 0.f;
+        for (int b = a + 1; b < M; b++) lvl += wrap_diff_n(phi[a], phi[b]);
+        tot = lvl + tot;
+      }
+      const float mean_diff = npairs > 0 ? tot / (float)npairs : __int_as_float(0x7fc00000);
+      guard *= 2.0f / (float)M;
+      unsigned fl = 0;
+      bool doubt = false;
+      const float thr = p.thr_phase_mag;
+      if (kGate) {
+        if (magsum > thr) fl |= 1;
+        if (fabsf(magsum - thr) <= 2.0e-5f * esum + 1.0e-6f * thr) doubt = true;
+      } else {
+        fl |= 1;
+      }
+      if (mean_diff < p.min_phase_rad) fl |= 2;
+      if (fabsf(mean_diff - p.min_phase_rad) <= guard && magsum > 1.0e-4f * esum) doubt = true;
+      if (doubt && p.win_d != nullptr) sc.recheck[atomicAdd(&sc.n_recheck, 1)] = (unsigned short)(l * 2 + f);
+      sc.flag[f][l] = (unsigned char)fl;
+    }
+  }
+  __syncthreads();
+  for (int q = warp; q < sc.n_recheck; q += kGenThreads / 32) {
+    const int l = sc.recheck[q] >> 1, f = sc.recheck[q] & 1;
+    const unsigned fl = phase_decide_fp64_n<NN>(p, s, t, l, f, lane, kGate);
+    if (lane == 0) sc.flag[f][l] = (unsigned char)fl;
+  }
+  __syncthreads();
+  // ---- per-bin output; phasempf: MCRA + bi-channel post-filter, state in global memory ([7][L], bin fastest) ----
+  int cl = cur_L, fst = first_L;
+  float* stg = (ALGO == ALGO_PHASEMPF) ? p.mpf_state + (size_t)s * 7 * L : nullptr;
+  for (int f = 0; f < nf; f++) {
+    bool reset_branch = false;
+    if (ALGO == ALGO_PHASEMPF) {   // phasempf.cpp:162-176: window bookkeeping is global per frame
+      reset_branch = cl > p.mcra_L;
+      if (reset_branch) { cl = 1; fst = 0; } else { cl++; }
+    }
+    const float inv_cl = 1.0f / (float)cl;
+    for (int l = tid; l < L; l += kGenThreads) {
+      float2 y = make_float2(0.f, 0.f);
+      if (l == 0) {
+        if (ALGO == ALGO_PHASE) y = unpack_n<NN>(zall, 0, f);   // phase.cpp:87; phasempf leaves bin 0 at 0 (SURVEY B-5)
+        sc.y[f][l] = y;
+        continue;
+      }
+      float magsum = 0.f;
+      float2 x0 = make_float2(0.f, 0.f);
+      for (int ch = 0; ch < M; ch++) {
+        const float2 x = unpack_n<NN>(zall + (size_t)ch * NN, l, f);
+        if (ch == 0) x0 = x;
+        magsum += sqrtf(fmaf(x.x, x.x, x.y * x.y));
+      }
+      const float mag_mean = magsum / (float)M;
+      const float a0 = sqrtf(fmaf(x0.x, x0.x, x0.y * x0.y));
+      const float2 unit = a0 > 0.f ? make_float2(x0.x / a0, x0.y / a0) : make_float2(1.f, 0.f);   // e^{i arg X_0}
+      const unsigned fl = sc.flag[f][l];
+      if (ALGO == ALGO_PHASE) {
+        const float mag = ((fl & 1) && (fl & 2)) ? mag_mean : mag_mean * p.mag_mult;   // phase.cpp:114-123
+        y = make_float2(mag * unit.x, mag * unit.y);
+      } else {
+        const bool kept = (fl & 2) != 0;
+        const float soi = kept ? mag_mean : mag_mean * p.min_mag;   // phasempf.cpp:234-244
+        const float itf = kept ? mag_mean * p.min_mag : mag_mean;
+        const float s2 = soi * soi, i2 = itf * itf;
+        const float Sf = (l == 1) ? 0.75f * s2 : s2;   // SURVEY B-9: only bins 1 and N-1 are scaled
+        float S_prev = stg[0 * L + l], S_tmp = stg[1 * L + l], S_min = stg[2 * L + l], lam = stg[3 * L + l];
+        const float S = p.mcra_alphaS * S_prev + (1.0f - p.mcra_alphaS) * Sf;
+        if (reset_branch) { S_min = fminf(S_tmp, S); S_tmp = S; }
+        else { S_min = fminf(S_min, S); S_tmp = fminf(S_tmp, S); }
+        if (fst || S < S_min * p.mcra_delta || lam > s2) {
+          if (fst && inv_cl > p.mcra_alphaD) lam = inv_cl * lam + (1.0f - inv_cl) * s2;
+          else lam = p.mcra_alphaD2 * lam + (1.0f - p.mcra_alphaD) * s2;   // SURVEY B-16
+        }
+        stg[0 * L + l] = S; stg[1 * L + l] = S_tmp; stg[2 * L + l] = S_min; stg[3 * L + l] = lam;
+        const float Z = p.mpf_alphaS * stg[4 * L + l] + (1.0f - p.mpf_alphaS) * i2;   // phasempf.cpp:255-271
+        const float rev0 = p.mpf_gamma * stg[5 * L + l] + p.mpf_rev_gain * s2;
+        const float rev1 = p.mpf_gamma * stg[6 * L + l] + p.mpf_rev_gain * i2;
+        stg[4 * L + l] = Z; stg[5 * L + l] = rev0; stg[6 * L + l] = rev1;
+        const float Lam = sqrtf(lam + p.mpf_eta * Z + rev0 + rev1);
+        float mag;
+        if (p.out_only_noise) {
+          mag = Lam * p.out_amp;
+        } else {
+          mag = p.out_only_mcra ? (soi - sqrtf(lam)) * p.out_amp : (soi - Lam) * p.out_amp;
+          if (mag < 0.f) mag = p.noise_floor;
+        }
+        const float2 u2 = soi > 0.f ? unit : make_float2(1.f, 0.f);
+        y = make_float2(mag * u2.x, mag * u2.y);
+      }
+      sc.y[f][l] = y;
+    }
+    // the same thread owns bin l in both frames (same loop mapping), so the state needs no barrier between frames
+  }
+  cur_L = cl;
+  first_L = fst;
+  __syncthreads();
+}
+
+template <int ALGO, int NN>
+__global__ void __launch_bounds__(kGenThreads, 1) frames_kernel_n(const KernelParams p) {
+  constexpr int H = NN / 2, L = NN / 2 + 2;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float2* zall = reinterpret_cast<float2*>(smem_raw);          // [M][NN]
+  float2* gbuf = zall + (size_t)p.M * NN;                       // [NN]
+  GenScratch<NN>& sc = *reinterpret_cast<GenScratch<NN>*>(gbuf + NN);
+  constexpr bool kPha = (ALGO == ALGO_PHASE || ALGO == ALGO_PHASEMPF);
+  constexpr bool kSmooth = (ALGO == ALGO_PHASEMPF);
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int M = p.M;
+  const int s = blockIdx.x + p.stream_begin;
+  const float2* tw = p.twid_f;
+  const float* win = p.win_f;
+  int cur_L = p.mcra_cur_L0, first_L = p.mcra_first0;
+
+  for (int i = tid; i < H; i += kGenThreads) sc.tail[i] = p.tail[(size_t)s * H + i];
+  if (kSmooth)
+    for (int i = tid; i < p.smooth_size - 1; i += kGenThreads) sc.ola[i] = p.smooth_hist[(size_t)s * 64 + i];
+  __syncthreads();
+
+  const int nh = p.hop_end - p.hop_begin;
+  const int npairs = (nh + 1) >> 1;
+  for (int ip = 0; ip < npairs; ip++) {
+    const int t = p.hop_begin + 2 * ip;
+    const bool two = t + 1 < p.hop_end;
+    if (tid < 2 * BF_MAX_MICS_DEV) (&sc.esum[0][0])[tid] = 0.f;
+    if (tid == 0) sc.n_recheck = 0;
+    __syncthreads();
+    // ---- window + pack: z = 0.5*w*(frame_t + i*frame_{t+1}), frame_t = [hop t-1 | hop t] (util.h:217-242) ----
+    for (int ch = 0; ch < M; ch++) {
+      const float* base = p.in + (size_t)s * p.in_stream_stride + (size_t)ch * p.in_mic_stride;
+      const float* ha = (t - 1 < 0) ? p.prev_hop + ((size_t)s * M + ch) * H : base + (size_t)(t - 1) * H;
+      const float* hb = base + (size_t)t * H;
+      const float* hc = two ? base + (size_t)(t + 1) * H : hb;
+      float e0 = 0.f, e1 = 0.f;
+      for (int n = tid; n < NN; n += kGenThreads) {
+        const float w = 0.5f * __ldg(win + n);
+        const float ft = (n < H) ? __ldg(ha + n) : __ldg(hb + n - H);
+        const float ft1 = !two ? 0.f : ((n < H) ? __ldg(hb + n) : __ldg(hc + n - H));
+        const float2 z = make_float2(ft * w, ft1 * w);
+        zall[(size_t)ch * NN + n] = z;
+        e0 = fmaf(z.x, z.x, e0);
+        e1 = fmaf(z.y, z.y, e1);
+      }
+      if (kPha) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { e0 += __shfl_xor_sync(0xffffffffu, e0, o); e1 += __shfl_xor_sync(0xffffffffu, e1, o); }
+        if (lane == 0) { atomicAdd(&sc.esum[0][ch], e0); atomicAdd(&sc.esum[1][ch], e1); }
+      }
+    }
+    __syncthreads();
+    if (kPha && tid < M) { sc.sqrtE[0][tid] = 2.0f * sqrtf(sc.esum[0][tid]); sc.sqrtE[1][tid] = 2.0f * sqrtf(sc.esum[1][tid]); }
+    block_fft<NN, -1>(zall, M, tw, tid);   // begins and ends with block barriers
+    // ---- per-bin beamformer ----
+    if (ALGO == ALGO_DAS) {
+      // das.cpp:60-63 commutes with the frame packing: G[j] = sum_i ceff_i[j] * Z_i[j] over all N bins
+      for (int j = tid; j < NN; j += kGenThreads) {
+        float2 acc = make_float2(0.f, 0.f);
+        for (int ch = 0; ch < M; ch++) {
+          const float2 z = zall[(size_t)ch * NN + j];
+          const float2 w = __ldg(p.das_ceff + (size_t)ch * NN + j);
+          acc.x = fmaf(z.x, w.x, acc.x); acc.x = fmaf(-z.y, w.y, acc.x);
+          acc.y = fmaf(z.x, w.y, acc.y); acc.y = fmaf(z.y, w.x, acc.y);
+        }
+        gbuf[j] = make_float2(2.0f * acc.x, 2.0f * acc.y);
+      }
+    } else {
+      phase_pair_n<ALGO, NN>(p, s, t, two, zall, sc, cur_L, first_L, tid);
+      for (int l = tid; l <= H; l += kGenThreads) {   // Hermitian assembly of G = Yh_t + i Yh_{t+1}
+        float2 y0 = sc.y[0][l], y1 = two ? sc.y[1][l] : make_float2(0.f, 0.f);
+        if (l == H - 1) {
+          const float2 p0 = sc.y[0][L - 1], p1 = two ? sc.y[1][L - 1] : make_float2(0.f, 0.f);
+          y0 = make_float2(0.5f * (y0.x + p0.x), 0.5f * (y0.y - p0.y));
+          y1 = make_float2(0.5f * (y1.x + p1.x), 0.5f * (y1.y - p1.y));
+        }
+        if (l == 0 || l == H) { y0.y = 0.f; y1.y = 0.f; }
+        gbuf[l] = make_float2(y0.x - y1.y, y0.y + y1.x);
+        if (l > 0 && l < H) gbuf[NN - l] = make_float2(y0.x + y1.y, y1.x - y0.y);
+      }
+      if (p.capture) {
+        for (int l = tid; l < L; l += kGenThreads)
+          for (int f = 0; f < (two ? 2 : 1); f++) {
+            unsigned char* cap = p.capture + (size_t)s * p.capture_stream_stride + (size_t)(t + f) * NN;
+            unsigned char fl = sc.flag[f][l];
+            fl = (unsigned char)(((fl & 1) && (fl & 2)) ? 2 : 0);
+            if (l <= H) {
+              cap[l] = fl;
+              if (l > 0 && l < H - 1) cap[NN - l] = fl;
+            } else {
+              cap[H + 1] = fl;
+            }
+          }
+      }
+    }
+    __syncthreads();
+    block_fft<NN, 1>(gbuf, 1, tw, tid);
+    // ---- synthesis window, overlap-add (util.h:244-253, 301-302), optional smoother ----
+    float* o0 = p.out + (size_t)s * p.out_stream_stride + (size_t)t * H;
+    const int S1 = kSmooth ? p.smooth_size - 1 : 0;
+    for (int n = tid; n < H; n += kGenThreads) {
+      const float w0 = __ldg(win + n) * p.out_scale, w1 = __ldg(win + n + H) * p.out_scale;
+      const float2 a = gbuf[n], b = gbuf[n + H];
+      const float r0 = sc.tail[n] + a.x * w0;
+      if (kSmooth) sc.ola[S1 + n] = r0; else o0[n] = r0;
+      if (two) {
+        const float r1 = b.x * w1 + a.y * w0;
+        if (kSmooth) sc.ola[S1 + H + n] = r1; else o0[H + n] = r1;
+        sc.tail[n] = b.y * w1;
+      } else {
+        sc.tail[n] = b.x * w1;
+      }
+    }
+    if (kSmooth) {
+      // phasempf.cpp:78-83,122-130,331-334: every output sample becomes the mean of the last smooth_size OLA samples
+      __syncthreads();
+      const int cnt = two ? NN : H, S = p.smooth_size;
+      const double inv = 1.0 / (double)S;
+      for (int n = tid; n < cnt; n += kGenThreads) {
+        double acc = 0.0;
+        for (int k = 0; k < S; k++) acc += (double)sc.ola[n + k];
+        o0[n] = (float)(acc * inv);
+      }
+      __syncthreads();
+      float keep = 0.f;
+      if (tid < S1) keep = sc.ola[cnt + tid];
+      __syncthreads();
+      if (tid < S1) sc.ola[tid] = keep;
+    }
+    __syncthreads();
+  }
+  for (int i = tid; i < H; i += kGenThreads) p.tail[(size_t)s * H + i] = sc.tail[i];
+  if (kSmooth)
+    for (int i = tid; i < p.smooth_size - 1; i += kGenThreads) p.smooth_hist[(size_t)s * 64 + i] = sc.ola[i];
+}
+
+template <int NN>
+static size_t gen_smem(int M) { return sizeof(float2) * ((size_t)M * NN + NN) + sizeof(GenScratch<NN>) + 16; }
+
+size_t frames_kernel_n_smem(int N, int M) {
+  switch (N) {
+    case 512: return gen_smem<512>(M);
+    case 1024: return gen_smem<1024>(M);
+    case 2048: return gen_smem<2048>(M);
+    case 4096: return gen_smem<4096>(M);
+  }
+  return ~(size_t)0;
+}
+
+template <int ALGO, int NN>
+static cudaError_t launch_n(const KernelParams& p, cudaStream_t st) {
+  const size_t smem = gen_smem<NN>(p.M);
+  cudaError_t e = cudaFuncSetAttribute(frames_kernel_n<ALGO, NN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  frames_kernel_n<ALGO, NN><<<p.n_streams, kGenThreads, smem, st>>>(p);
+  return cudaGetLastError();
+}
+
+template <int ALGO>
+static cudaError_t launch_algo(const KernelParams& p, cudaStream_t st) {
+  switch (p.N) {
+    case 512: return launch_n<ALGO, 512>(p, st);
+    case 1024: return launch_n<ALGO, 1024>(p, st);
+    case 2048: return launch_n<ALGO, 2048>(p, st);
+    case 4096: return launch_n<ALGO, 4096>(p, st);
+  }
+  return cudaErrorNotSupported;
+}
+
+cudaError_t launch_frames_kernel_n(int algo, const KernelParams& p, cudaStream_t st) {
+  switch (algo) {
+    case ALGO_DAS: return launch_algo<ALGO_DAS>(p, st);
+    case ALGO_PHASE: return launch_algo<ALGO_PHASE>(p, st);
+    case ALGO_PHASEMPF: return launch_algo<ALGO_PHASEMPF>(p, st);
+  }
+  return cudaErrorNotSupported;
+}
+
+}   // namespace bf

@@ -62,6 +62,7 @@ struct SelShared {
   int n_items, n_recheck;
   unsigned char flag[2][kL1K];
   float tail[512];
+  int nonfinite[2][2];   // [pair parity][frame]: the frame's spectrum holds inf/NaN (cold start, SURVEY B-10)
   uint64_t bars[kSelWarps];
 };
 
@@ -327,7 +328,7 @@ __global__ void __launch_bounds__(kSelThreads, ALGO == ALGO_LCMV ? 1 : 2) sel_pa
 #pragma unroll
       for (int k2 = 0; k2 < 32; k2++) myz[k2 * 32 + lane] = v[k2];
     }
-    if (tid == 0) { sc.n_items = 0; sc.n_recheck = 0; }
+    if (tid == 0) { sc.n_items = 0; sc.n_recheck = 0; sc.nonfinite[ip & 1][0] = 0; sc.nonfinite[ip & 1][1] = 0; }
     __syncthreads();   // (a) Z complete; G of the previous pair complete
     const int fr0 = (p.ring_slot0 + (t - p.hop_begin)) % D;   // ring slot of frame t
     // ------------------------------------------------------------------ B1: gate, history append, defaults
@@ -422,11 +423,15 @@ __global__ void __launch_bounds__(kSelThreads, ALGO == ALGO_LCMV ? 1 : 2) sel_pa
       __syncwarp();
       sel_fft1024_fwd(v, sc.g, tw, lane);   // IFFT(G) = swap(FFT(swap(G))); G itself is the exchange tile
       float* o0 = p.out + (size_t)s * p.out_stream_stride + (size_t)tp * H;
+      // one inf/NaN bin makes the reference's whole inverse frame NaN; the two frames of a pair share one complex
+      // transform here, so a poisoned frame was zeroed in B3 and is re-poisoned now without touching its partner
+      const float bad0 = sc.nonfinite[(ip - 1) & 1][0] ? __int_as_float(0x7fc00000) : 0.f;
+      const float bad1 = sc.nonfinite[(ip - 1) & 1][1] ? __int_as_float(0x7fc00000) : 0.f;
       static_for<0, 16>([&](auto m2) {
         const float w0 = win1024<m2>(s_o, c_o);
         const float w1 = win1024<m2 + 16>(s_o, c_o);
-        const float y0a = v[m2].y * w0, y0b = v[m2 + 16].y * w1;   // frame t: first / second half
-        const float y1a = v[m2].x * w0, y1b = v[m2 + 16].x * w1;   // frame t+1
+        const float y0a = v[m2].y * w0 + bad0, y0b = v[m2 + 16].y * w1 + bad0;   // frame t: first / second half
+        const float y1a = v[m2].x * w0 + bad1, y1b = v[m2 + 16].x * w1 + bad1;   // frame t+1
         o0[32 * m2 + lane] = sc.tail[32 * m2 + lane] + y0a;        // util.h:301-302
         if (ptwo) o0[H + 32 * m2 + lane] = y0b + y1a;
         sc.tail[32 * m2 + lane] = ptwo ? y1b : y0b;
@@ -474,12 +479,24 @@ __global__ void __launch_bounds__(kSelThreads, ALGO == ALGO_LCMV ? 1 : 2) sel_pa
       issue(t + 2);
     }
     // ------------------------------------------------------------------ B3: Hermitian assembly, diagnostics
+    if (live && (ALGO == ALGO_MVDR || ALGO == ALGO_LCMV)) {
+      bool b0 = false, b1 = false;
+      for (int l = tid; l < kL1K; l += kSelThreads) {
+        const float2 y0 = sc.y[0][l], y1 = sc.y[1][l];
+        b0 |= !(isfinite(y0.x) && isfinite(y0.y));
+        b1 |= two && !(isfinite(y1.x) && isfinite(y1.y));
+      }
+      if (b0) sc.nonfinite[ip & 1][0] = 1;
+      if (b1) sc.nonfinite[ip & 1][1] = 1;
+      __syncthreads();
+    }
     if (live) {
+      const bool z0 = sc.nonfinite[ip & 1][0] != 0, z1 = sc.nonfinite[ip & 1][1] != 0;
       for (int l = tid; l < kL1K; l += kSelThreads) {
         if (l <= 512) {
-          float2 y0 = sc.y[0][l], y1 = two ? sc.y[1][l] : make_float2(0.f, 0.f);
+          float2 y0 = z0 ? make_float2(0.f, 0.f) : sc.y[0][l], y1 = (two && !z1) ? sc.y[1][l] : make_float2(0.f, 0.f);
           if (l == 511) {   // Hermitian part of the asymmetric pair (N/2-1, N/2+1): Yh = (Y[N/2-1] + conj(Y[N/2+1])) / 2
-            const float2 p0 = sc.y[0][kL1K - 1], p1 = two ? sc.y[1][kL1K - 1] : make_float2(0.f, 0.f);
+            const float2 p0 = z0 ? make_float2(0.f, 0.f) : sc.y[0][kL1K - 1], p1 = (two && !z1) ? sc.y[1][kL1K - 1] : make_float2(0.f, 0.f);
             y0 = make_float2(0.5f * (y0.x + p0.x), 0.5f * (y0.y - p0.y));
             y1 = make_float2(0.5f * (y1.x + p1.x), 0.5f * (y1.y - p1.y));
           }

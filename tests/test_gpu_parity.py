@@ -189,3 +189,54 @@ def test_phasempf_split_calls_carry_state():
     b = bf.Beamformer(cfg, n_streams=2)
     got = np.concatenate([b.process(x[:, :, :33 * H]), b.process(x[:, :, 33 * H:34 * H]), b.process(x[:, :, 34 * H:])], axis=1)
     assert rel_l2(got, ref) <= REL_L2_TOL
+
+
+# ---------------------------------------------------------------------------------------------
+# golden vectors: outputs of the reference's own (unmodified) node sources, tests/golden/make_golden.py
+# ---------------------------------------------------------------------------------------------
+import os as _os
+
+from golden.cases import CASES as GOLDEN_CASES, build_case as golden_build_case
+
+_GOLD = np.load(_os.path.join(_os.path.dirname(_os.path.abspath(__file__)), "golden", "ref_outputs.npz"))
+
+
+@pytest.mark.parametrize("name", sorted(GOLDEN_CASES))
+def test_gpu_matches_reference_golden(name):
+    """Every golden case (all six nodes; 512-, 1024- and 4096-point frames; theta / interference events; the
+    cold-start NaN case) through the C ABI against the reference's output."""
+    cfg, x, events = golden_build_case(name)
+    ref = _GOLD[name + "/out"]
+    b = bf.Beamformer(cfg, n_streams=1)
+    got = b.process(x[None], events=events)[0]
+    assert got.shape == ref.shape
+    err = finite_rel_l2(got, ref)
+    print(name, "rel_l2 vs reference", err)
+    assert err <= REL_L2_TOL
+    assert b.interferences == list(_GOLD[name + "/interf"]), "interference list must be bit-exact"
+
+
+@pytest.mark.parametrize("algo,mics,hop,kw", [("das", "aira3", 256, {}), ("das", "circ8", 1024, {}), ("das", "binaural", 2048, {}),
+                                              ("phase", "aira3", 256, dict(mag_threshold=0.002)), ("phase", "binaural", 2048, dict(mag_threshold=0.002)),
+                                              ("phasempf", "binaural", 2048, {}), ("phasempf", "aira3", 1024, dict(out_only_mcra=True))])
+def test_other_frame_sizes_match_oracle(algo, mics, hop, kw):
+    # 512- to 4096-point frames (JACK periods 256..2048) run the frame-size-generic kernel
+    cfg = bf.make_config(algo, mics=mics, hop=hop, initial_angle=15.0, **kw)
+    n_hops = 61 if algo != "phasempf" else 130
+    x = np.stack([synth_stream(bf.GEOMETRIES[mics], n_hops * hop, seed=300 + b, gate_hz=1.3 if algo == "phasempf" else 0.0) for b in range(2)])
+    ref = oracle_batch(cfg, x)
+    b = bf.Beamformer(cfg, n_streams=2)
+    k = 20 * hop
+    got = np.concatenate([b.process(x[:, :, :k]), b.process(x[:, :, k:k + hop]), b.process(x[:, :, k + hop:])], axis=1)   # state carried across calls
+    err = rel_l2(got, ref)
+    print(algo, mics, "hop", hop, "rel_l2", err)
+    assert err <= REL_L2_TOL
+
+
+def test_unsupported_shapes_fail_loudly():
+    with pytest.raises(bf.BeamformError):
+        bf.Beamformer(bf.make_config("mvdr", mics="circ8", hop=2048), 1)      # mvdr is built for 1024-point frames
+    with pytest.raises(bf.BeamformError):
+        bf.Beamformer(bf.make_config("das", mics="circ8", hop=2048), 1)       # 8 x 4096-point spectra exceed shared memory
+    with pytest.raises(bf.BeamformError):
+        bf.Beamformer(bf.make_config("das", mics="aira3", hop=300), 1)
