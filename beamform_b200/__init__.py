@@ -233,6 +233,13 @@ class Beamformer:
         _check(lib().bf_process_batch_device(self._h, in_ptr, in_stream_stride or self.n_mics * L, in_mic_stride or L, out_ptr,
                                              out_stream_stride or L, n_hops, ev, nev, stream_ptr), "bf_process_batch_device")
 
+    def srp_device(self, in_ptr, thetas_deg, maps_ptr, n_hops, stream_ptr=0, in_stream_stride=None, in_mic_stride=None):
+        """Steered-response power maps [B][n_hops][len(thetas)] float32 (device) for look directions `thetas_deg`."""
+        L = n_hops * self.hop
+        th = np.ascontiguousarray(thetas_deg, dtype=np.float32)
+        _check(lib().bf_srp_batch_device(self._h, in_ptr, in_stream_stride or self.n_mics * L, in_mic_stride or L,
+                                         th.ctypes.data_as(C.POINTER(C.c_float)), len(th), maps_ptr, n_hops, stream_ptr), "bf_srp_batch_device")
+
     def set_capture(self, dev_ptr):
         _check(lib().bf_set_capture(self._h, dev_ptr), "bf_set_capture")
 

@@ -32,6 +32,8 @@ bool sel_pairs_supported(const KernelParams& p, int algo);
 cudaError_t launch_sel_pairs(int algo, const KernelParams& p, cudaStream_t st);
 cudaError_t launch_frames_kernel_n(int algo, const KernelParams& p, cudaStream_t st);
 size_t frames_kernel_n_smem(int N, int M);
+cudaError_t launch_srp(const KernelParams& p, float2* xs, const double* tau, const double* freqs_l, float* maps, int D, int n_hops,
+                       cudaStream_t st);
 }   // namespace bf
 
 typedef std::complex<double> cd;
@@ -86,6 +88,12 @@ struct bf_handle {
   int Lsel = 0;
   float2* d_hist = nullptr;     // mvdr/lcmv: [B][Lsel][P+2][M]
   float2* d_gss_w = nullptr;    // gss: [B][Lsel][C][M]
+  // steered-response sweep workspace
+  float2* d_srp_xs = nullptr;
+  size_t srp_xs_cap = 0;
+  double* d_srp_tau = nullptr;
+  size_t srp_tau_cap = 0;
+  double* d_srp_freqs = nullptr;
   float* d_win_f = nullptr;
   float2* d_twid_f = nullptr;
   double* d_win_d = nullptr;
@@ -489,6 +497,7 @@ extern "C" void bf_destroy(bf_handle* h) {
   for (int i = 0; i < 8; i++) { if (h->ev_in[i]) cudaEventDestroy(h->ev_in[i]); if (h->ev_k[i]) cudaEventDestroy(h->ev_k[i]); }
   cudaFree(h->d_steer_d); cudaFree(h->d_mpf_state); cudaFree(h->d_smooth_hist);
   cudaFree(h->d_sel_slot); cudaFree(h->d_sel_list); cudaFree(h->d_hist); cudaFree(h->d_gss_w); cudaFree(h->d_win_d); cudaFree(h->d_twid_d); cudaFree(h->d_win_f); cudaFree(h->d_twid_f);
+  cudaFree(h->d_srp_xs); cudaFree(h->d_srp_tau); cudaFree(h->d_srp_freqs);
   if (h->h_stage_in) cudaFreeHost(h->h_stage_in);
   if (h->h_stage_out) cudaFreeHost(h->h_stage_out);
   delete h;
@@ -783,8 +792,45 @@ extern "C" int bf_set_capture(bf_handle* h, uint8_t* dev_flags) {
   return BF_OK;
 }
 
-extern "C" int bf_srp_batch_device(bf_handle*, const float*, size_t, size_t, const float*, uint32_t, float*, uint32_t, void*) {
-  return fail(BF_ERR_INVALID, "bf_srp_batch_device: not built yet");
+// Steered-response sweep (config C5).  Stateless with respect to the beamformer: frame 0 uses the handle's
+// "previous hop" state (zeros before the first process call) and nothing is advanced.
+extern "C" int bf_srp_batch_device(bf_handle* h, const float* in_dev, size_t ss, size_t ms, const float* thetas_deg_host, uint32_t n_dirs,
+                                   float* maps_dev, uint32_t n_hops, void* cuda_stream) {
+  if (!h || !in_dev || !thetas_deg_host || !maps_dev) return fail(BF_ERR_INVALID, "bf_srp_batch_device: null argument");
+  if (h->N != 1024) return fail(BF_ERR_INVALID, "bf_srp_batch_device: built for 1024-point frames (hop 512)");
+  if (n_dirs < 1 || n_hops < 1) return fail(BF_ERR_INVALID, "bf_srp_batch_device: empty sweep");
+  CUDA_TRY(cudaSetDevice(h->dev));
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  const size_t F = (size_t)h->B * n_hops;
+  const size_t need_xs = (size_t)h->L * F * h->M;
+  if (need_xs > h->srp_xs_cap) {
+    if (h->d_srp_xs) cudaFree(h->d_srp_xs);
+    h->d_srp_xs = nullptr; h->srp_xs_cap = 0;
+    if (cudaMalloc(&h->d_srp_xs, sizeof(float2) * need_xs) != cudaSuccess) return fail(BF_ERR_ALLOC, "bf_srp_batch_device: spectra workspace");
+    h->srp_xs_cap = need_xs;
+  }
+  const size_t need_tau = (size_t)n_dirs * h->M;
+  if (need_tau > h->srp_tau_cap) {
+    if (h->d_srp_tau) cudaFree(h->d_srp_tau);
+    h->d_srp_tau = nullptr; h->srp_tau_cap = 0;
+    if (cudaMalloc(&h->d_srp_tau, sizeof(double) * need_tau) != cudaSuccess) return fail(BF_ERR_ALLOC, "bf_srp_batch_device: delay table");
+    h->srp_tau_cap = need_tau;
+  }
+  if (!h->d_srp_freqs && cudaMalloc(&h->d_srp_freqs, sizeof(double) * h->L) != cudaSuccess) return fail(BF_ERR_ALLOC, "bf_srp_batch_device: freq table");
+  std::vector<double> tau(need_tau), fl(h->L);
+  for (uint32_t d = 0; d < n_dirs; d++) calculate_delays(h, (double)thetas_deg_host[d], tau.data() + (size_t)d * h->M);   // util.h:136-161
+  for (uint32_t l = 0; l < h->L; l++) fl[l] = h->freqs[l];   // logical bin N/2+1 is FFT bin N/2+1 itself
+  CUDA_TRY(cudaMemcpyAsync(h->d_srp_tau, tau.data(), sizeof(double) * need_tau, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaMemcpyAsync(h->d_srp_freqs, fl.data(), sizeof(double) * h->L, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaStreamSynchronize(st));   // host tables go out of scope
+  bf::KernelParams p;
+  memset(&p, 0, sizeof(p));
+  p.in = in_dev; p.in_stream_stride = (long long)ss; p.in_mic_stride = (long long)ms;
+  p.n_streams = h->B; p.M = h->M; p.H = h->H; p.N = h->N;
+  p.prev_hop = h->d_prev_hop;
+  CUDA_TRY(bf::launch_srp(p, h->d_srp_xs, h->d_srp_tau, h->d_srp_freqs, maps_dev, (int)n_dirs, (int)n_hops, st));
+  h->launches += 2;
+  return BF_OK;
 }
 
 extern "C" int bf_set_profiling(bf_handle* h, int enabled) {

@@ -29,18 +29,23 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np
 
 SR = 48000
-H = 512
+H = 512   # default JACK period; a workload may override it ("hop")
 
 WORKLOADS = {
-    # BASELINE.json configs[1]: the configuration the metric is quoted on
+    # BASELINE.json configs[1]: the configuration the metric is quoted on.  1184 = 8 x 148 streams ("batched 1k streams"):
+    # the mvdr kernel keeps two streams resident per SM, so a multiple of 296 leaves no partially filled last wave.
     "c2": dict(name="C2: MVDR 8-mic 1024-pt, energy-thresholded bins, batched synthetic streams", algo="mvdr", mics="circ8",
-               n_streams=1024, hops_per_step=188, interferers=()),
+               n_streams=1184, hops_per_step=188, interferers=(), kernel="sel_pairs_kernel<mvdr>"),
     "c1": dict(name="C1: DAS 3-mic (aira3) 1024-pt, batched synthetic streams", algo="das", mics="aira3", n_streams=2048,
-               hops_per_step=188, interferers=()),
-    "c3l": dict(name="C3: LCMV 8-mic, 3 interferers", algo="lcmv", mics="circ8", n_streams=1024, hops_per_step=188,
-                interferers=(80.0, -60.0, 150.0)),
-    "c3g": dict(name="C3: GSS 8-mic, 3 interferers", algo="gss", mics="circ8", n_streams=1024, hops_per_step=188,
-                interferers=(80.0, -60.0, 150.0)),
+               hops_per_step=188, interferers=(), kernel="das_pairs_kernel<8>"),
+    "c3l": dict(name="C3: LCMV 8-mic, 3 interferers", algo="lcmv", mics="circ8", n_streams=1184, hops_per_step=188,
+                interferers=(80.0, -60.0, 150.0), kernel="sel_pairs_kernel<lcmv>"),
+    "c3g": dict(name="C3: GSS 8-mic, 3 interferers", algo="gss", mics="circ8", n_streams=1184, hops_per_step=188,
+                interferers=(80.0, -60.0, 150.0), kernel="sel_pairs_kernel<gss>"),
+    "c4": dict(name="C4: PhaseMPF 2-mic (binaural) 4096-pt, phase mask + MCRA bi-channel post-filter", algo="phasempf", mics="binaural",
+               n_streams=1184, hops_per_step=47, hop=2048, interferers=(), kernel="frames_kernel_n<phasempf,4096>"),
+    "ph": dict(name="Phase 3-mic (aira3) 1024-pt phase mask", algo="phase", mics="aira3", n_streams=1184, hops_per_step=188,
+               interferers=(), kernel="frames_kernel_1024<phase>"),
 }
 
 
@@ -103,22 +108,49 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(self.reasons)}
 
 
-def run_cpu_reference(cfg, mic_xy, n_sample_streams, hops, seed, threads):
-    """Times the CPU restatement (oracle/) on `threads` host threads: audio-seconds per second."""
-    from beamform_b200.synth import synth_batch
-    from oracle_lib import Oracle, lib as oracle_lib
-    oracle_lib()
-    x = synth_batch(mic_xy, n_sample_streams, hops * H, seed=seed)
+def cpu_kind(algo):
+    import ref_lib
+    return "reference" if ref_lib.available(algo) else "port"
 
-    def one(b):
-        Oracle(cfg).process(x[b])
-        return 0
+
+def run_cpu_reference(cfg, algo, mic_xy, n_sample_streams, hops, seed, threads, hop=H):
+    """Times the reference's CPU path on `threads` host threads: audio-seconds per second.  Uses the reference's own node
+    binaries (oracle/_ref, unmodified sources against oracle/shim) when they travelled with the tree, else the oracle port."""
+    from beamform_b200.synth import synth_batch
+    import ref_lib
+    x = synth_batch(mic_xy, n_sample_streams, hops * hop, seed=seed)
+    if ref_lib.available(algo):
+        def one(b):
+            ref_lib.run_ref(algo, cfg, x[b])
+            return 0
+    else:
+        from oracle_lib import Oracle, lib as oracle_lib
+        oracle_lib()
+
+        def one(b):
+            Oracle(cfg).process(x[b])
+            return 0
 
     t0 = time.perf_counter()
     with ThreadPoolExecutor(max_workers=threads) as ex:
         list(ex.map(one, range(n_sample_streams)))
     dt = time.perf_counter() - t0
-    return n_sample_streams * hops * H / SR / dt, dt
+    return n_sample_streams * hops * hop / SR / dt, dt
+
+
+def cpu_sample(cfg, algo, mic_xy, cores, seed, hop=H, target_s=15.0):
+    """Bounded CPU sample of the workload: calibrate on one short stream per core, then size the sample for about
+    target_s seconds of wall time, capped at 4 streams per core x 376 hops (generating more synthetic audio than
+    that would dominate the run for the cheap nodes)."""
+    unit = max(1, 512 // hop * 94 // 94) if hop <= 512 else 1
+    hops0 = max(6, 24 * 512 // hop)
+    v0, dt0 = run_cpu_reference(cfg, algo, mic_xy, cores, hops0, seed, cores, hop)
+    per_stream_hop = dt0 / hops0                      # wall seconds per hop when every core runs one stream
+    hops = int(min(376 * 512 // hop, max(hops0, target_s / max(per_stream_hop, 1e-9))))
+    rounds = int(min(4, max(1, round(target_s / max(per_stream_hop * hops, 1e-9)))))
+    nstr = cores * rounds
+    v, dt = run_cpu_reference(cfg, algo, mic_xy, nstr, hops, seed + 1, cores, hop)
+    return v, dt, "%d streams x %d hops (%.1f s audio) of the same workload, %d threads, %.1f s wall" % (nstr, hops, nstr * hops * hop / SR, cores, dt)
 
 
 def main():
@@ -146,6 +178,7 @@ def main():
     mic_xy = bf.GEOMETRIES[wl["mics"]]
     M = len(mic_xy)
     B, T = wl["n_streams"], wl["hops_per_step"]
+    H = wl.get("hop", 512)
     cores = os.cpu_count() or 1
     config = {"workload": wl["name"], "algo": wl["algo"], "n_mics": M, "fft_win": 2 * H, "hop": H, "sample_rate": SR,
               "streams_per_gpu": B, "hops_per_step": T, "audio_s_per_step_per_gpu": B * T * H / SR,
@@ -154,25 +187,25 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return 0
-        cfg = bf.make_config(wl["algo"], mics=wl["mics"], interferers=wl["interferers"])
-        hops = 94
-        nstr = cores * 2
+        cfg = bf.make_config(wl["algo"], mics=wl["mics"], hop=H, interferers=wl["interferers"])
+        kind = cpu_kind(wl["algo"])
         for _ in range(max(0, min(args.warmup, 1))):
-            run_cpu_reference(cfg, mic_xy, cores, 24, 5, cores)
+            run_cpu_reference(cfg, wl["algo"], mic_xy, cores, max(8, 24 * 512 // H), 5, cores, H)
         vals, t_tot = [], 0.0
-        for k in range(args.steps):
-            v, dt = run_cpu_reference(cfg, mic_xy, nstr, hops, 100 + k, cores)
+        sample = ""
+        for k in range(args.steps):   # each step: a bounded sample of the workload, ~60 s total over the run
+            v, dt, sample = cpu_sample(cfg, wl["algo"], mic_xy, cores, 100 + 7 * k, H, target_s=max(4.0, 60.0 / max(1, args.steps)))
             vals.append(v)
             t_tot += dt
         value = float(np.mean(vals))
-        sample = "%d streams x %d hops (%.1f s audio) per step on %d threads" % (nstr, hops, nstr * hops * H / SR, cores)
         print(json.dumps({
             "impl": "reference", "metric": "beamformed audio-sec/sec", "value": value, "unit": "audio-s/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_tot / max(1, args.steps), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
-            "cpu_baseline": {"value": value, "unit": "audio-s/s", "cores": cores, "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": value, "unit": "audio-s/s", "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": value, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "note": "reference CPU path, restated (own FFT/LU in double; FFTW/Eigen/JACK/ROS are not installable here)"}))
+            "note": ("reference node sources compiled unmodified against oracle/shim (FFTW/Eigen/JACK/ROS stand-ins: own FFT and LU)"
+                     if kind == "reference" else "CPU restatement of the reference (oracle port); oracle/_ref was not shipped")}))
         return 0
 
     import torch
@@ -181,7 +214,7 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    cfg = bf.make_config(wl["algo"], mics=wl["mics"], interferers=wl["interferers"], device=local_rank)
+    cfg = bf.make_config(wl["algo"], mics=wl["mics"], hop=H, interferers=wl["interferers"], device=local_rank)
     beam = bf.Beamformer(cfg, n_streams=B)
     L = T * H
     x = device_synth(torch, mic_xy, B, L, seed=0xBEA4F0 + 1000 * rank, device=dev)
@@ -266,17 +299,15 @@ def main():
             pass
         cpu = None
         if not args.no_cpu and world == 1:
-            nstr = cores * 2
-            v, dt = run_cpu_reference(cfg, mic_xy, nstr, 94, 77, cores)
-            cpu = {"value": v, "unit": "audio-s/s", "cores": cores, "kind": "port",
-                   "sample": "%d streams x 94 hops (%.1f s audio) of the same workload, %d threads, %.1f s wall" % (nstr, nstr * 94 * H / SR, cores, dt)}
+            v, dt, sample = cpu_sample(cfg, wl["algo"], mic_xy, cores, 77, H, target_s=15.0)
+            cpu = {"value": v, "unit": "audio-s/s", "cores": cores, "kind": cpu_kind(wl["algo"]), "sample": sample}
         out = {
             "metric": "beamformed audio-sec/sec", "value": value, "unit": "audio-s/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32 (lcmv solves f64)" if wl["algo"] == "lcmv" else "f32", "data": "synthetic", "config": config,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
                          "traffic": traffic, "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650",
-                         "kernel": "frames_kernel_1024<%s>" % wl["algo"], "kernel_ms_per_launch": kern_ms / max(1, kern_n),
+                         "kernel": wl.get("kernel", "frames_kernel_1024<%s>" % wl["algo"]), "kernel_ms_per_launch": kern_ms / max(1, kern_n),
                          "algorithmic_bytes_per_launch": alg_bytes_per_launch},
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
         }

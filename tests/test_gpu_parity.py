@@ -240,3 +240,31 @@ def test_unsupported_shapes_fail_loudly():
         bf.Beamformer(bf.make_config("das", mics="circ8", hop=2048), 1)       # 8 x 4096-point spectra exceed shared memory
     with pytest.raises(bf.BeamformError):
         bf.Beamformer(bf.make_config("das", mics="aira3", hop=300), 1)
+
+
+# ---------------------------------------------------------------------------------------------
+# steered-response sweep (config C5)
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("mics,n_dirs,n_hops", [("grid64", 360, 9), ("circ8", 72, 12), ("aira3", 10, 5)])
+def test_srp_maps_match_oracle(mics, n_dirs, n_hops):
+    import torch
+    cfg = bf.make_config("das", mics=mics)
+    xy = bf.GEOMETRIES[mics]
+    x = np.stack([synth_stream(xy, n_hops * H, seed=400 + b, sources=((25.0 + 40 * b, 0.1, 190.0, 20), (-100.0, 0.05, 233.0, 20)),
+                               lead_in=0) for b in range(2)])
+    thetas = -180.0 + 360.0 * np.arange(n_dirs) / n_dirs
+    b = bf.Beamformer(cfg, n_streams=2)
+    xin = torch.from_numpy(x).cuda()
+    maps = torch.zeros((2, n_hops, n_dirs), dtype=torch.float32, device="cuda")
+    b.srp_device(xin.data_ptr(), thetas, maps.data_ptr(), n_hops, stream_ptr=torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    got = maps.cpu().numpy().astype(np.float64)
+    ref = np.stack([Oracle(cfg).srp(x[s], thetas.astype(np.float32).astype(np.float64)) for s in range(2)])
+    err = rel_l2(got, ref)
+    print("srp", mics, "rel_l2", err)
+    assert err <= REL_L2_TOL
+    # the map peaks at the dominant source direction (within the sweep resolution and the array's beam width)
+    if mics == "grid64":
+        peak = thetas[int(np.argmax(ref[0, n_hops - 1]))]
+        assert abs(((peak - 25.0 + 180) % 360) - 180) <= 6.0
+        assert int(np.argmax(got[0, n_hops - 1])) == int(np.argmax(ref[0, n_hops - 1]))
