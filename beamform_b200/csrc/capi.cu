@@ -31,7 +31,7 @@ cudaError_t launch_das_pairs(const KernelParams& p, cudaStream_t st, int sm_coun
 bool sel_pairs_supported(const KernelParams& p, int algo);
 cudaError_t launch_sel_pairs(int algo, const KernelParams& p, cudaStream_t st);
 cudaError_t launch_frames_kernel_n(int algo, const KernelParams& p, cudaStream_t st);
-size_t frames_kernel_n_smem(int N, int M);
+size_t frames_kernel_n_smem(int N, int M, int algo);
 cudaError_t launch_srp(const KernelParams& p, float2* xs, const double* tau, const double* freqs_l, float* maps, int D, int n_hops,
                        cudaStream_t st);
 }   // namespace bf
@@ -361,7 +361,7 @@ extern "C" int bf_create(bf_handle** out, const bf_config* cfg, uint32_t n_strea
   if (cfg->hop != 512) {
     if (cfg->algo == BF_ALGO_MVDR || cfg->algo == BF_ALGO_LCMV || cfg->algo == BF_ALGO_GSS)
       return fail(BF_ERR_INVALID, "bf_create: mvdr/lcmv/gss are built for 1024-point frames (hop 512) only");
-    if (bf::frames_kernel_n_smem(2 * (int)cfg->hop, cfg->n_mics) > 232448)
+    if (bf::frames_kernel_n_smem(2 * (int)cfg->hop, cfg->n_mics, cfg->algo) > 232448)
       return fail(BF_ERR_INVALID, "bf_create: too many microphones for this frame size (spectra must fit 227 KB of shared memory)");
   }
   if (cfg->algo < 0 || cfg->algo > 5) return fail(BF_ERR_INVALID, "bf_create: unknown algo");

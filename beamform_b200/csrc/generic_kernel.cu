@@ -11,33 +11,54 @@
 // imaginary parts of one complex transform, spectra never leave shared memory and every input sample is
 // fetched from HBM once (its second touch hits L1/L2).
 //
+// Phase-mask nodes: their forward transforms run in FP64 (B200 issues DFMA at half the FFMA rate).  Every mask
+// decision (phase.cpp:114, phasempf.cpp:234) is a threshold on phases of individual bins, and with FP32 spectra a
+// few percent of the bins of a 4096-point frame fall inside the rounding guard band; re-deciding those from an exact
+// double DFT of the bin cost 7x the transforms themselves.  With double spectra the decision is taken in FP32
+// (atan2f) and only results within 2e-6 rad of the threshold are recomputed in double from the same spectra, O(M).
+//
 // The 1024-point frames of the headline configurations use the register-resident warp FFT kernels
 // (das_kernel.cu, sel_kernel.cu, frames_kernel.cu); this kernel covers the other frame sizes, notably the
 // 4096-point PhaseMPF configuration C4.
+#include <type_traits>
+
 #include "bf_device.h"
 #include "fft_reg.cuh"
+#include "fft_reg_d.cuh"
 
 namespace bf {
 
 constexpr int kGenThreads = 256;
 
+// XOR swizzle of a transform's element index (elements are 8 or 16 bytes): the first Stockham pass scatters with a
+// stride of R elements, which without it lands every lane of a warp in the same shared-memory bank group.
+__device__ __forceinline__ int swz(int idx) { return idx ^ ((idx >> 4) & 7); }
+
 template <int NN>
 struct GenScratch {
   static constexpr int L = NN / 2 + 2;
   float2 y[2][L];
-  float sqrtE[2][BF_MAX_MICS_DEV];
-  float esum[2][BF_MAX_MICS_DEV];
-  unsigned short recheck[2 * L];
-  int n_recheck;
   unsigned char flag[2][L];   // bit0: magnitude gate passed (phase.cpp:99), bit1: bin kept as source of interest
   float tail[NN / 2];
   float ola[64 + NN];         // phasempf: post-OLA moving-average window (smooth_size <= 64)
 };
 
+template <typename V> struct VecOps;
+template <> struct VecOps<float2> {
+  static __device__ __forceinline__ float2 mul(float2 a, float2 w) { return cmul(a, w); }
+  static __device__ __forceinline__ float2 mulc(float2 a, float2 w) { return cmulc(a, w); }
+  template <int R, int DIR> static __device__ __forceinline__ void fft(float2* v) { fft_dit<R, DIR>(v); }
+};
+template <> struct VecOps<double2> {
+  static __device__ __forceinline__ double2 mul(double2 a, double2 w) { return cmul_d(a, w); }
+  static __device__ __forceinline__ double2 mulc(double2 a, double2 w) { return cmulc_d(a, w); }
+  template <int R, int DIR> static __device__ __forceinline__ void fft(double2* v) { fft_dit_d<R, DIR>(v); }
+};
+
 // One Stockham pass of radix R over `nfft` transforms of size NN stored back to back in z (in place).
 //   j in [0, NN/R): k = j mod Ns; v[q] = z[j + q*NN/R] * W_{Ns*R}^{k q}; V = DFT_R(v); z[(j/Ns)*Ns*R + k + q*Ns] = V[q]
-template <int NN, int R, int DIR>
-__device__ __forceinline__ void stockham_pass(float2* z, int nfft, int Ns, const float2* __restrict__ tw, int tid) {
+template <int NN, int R, int DIR, typename V>
+__device__ __forceinline__ void stockham_pass(V* z, int nfft, int Ns, const V* __restrict__ tw, int tid) {
   constexpr int per = NN / R;                                  // tasks per transform
   constexpr int g = kGenThreads / per > 0 ? kGenThreads / per : 1;   // transforms per round
   static_assert(per <= kGenThreads, "one round must cover a whole transform");
@@ -48,60 +69,60 @@ __device__ __forceinline__ void stockham_pass(float2* z, int nfft, int Ns, const
   for (int f0 = 0; f0 < nfft; f0 += g) {
     const int f = f0 + f_local;
     const bool on = f_local < g && f < nfft;
-    float2 v[R];
-    float2* zz = z + (size_t)f * NN;
+    V v[R];
+    V* zz = z + (size_t)f * NN;
     if (on) {
 #pragma unroll
       for (int q = 0; q < R; q++) {
-        float2 a = zz[j + q * per];
+        V a = zz[swz(j + q * per)];
         if (q > 0) {
-          const float2 w = __ldg(tw + ((tstep * q) & (NN - 1)));
-          a = (DIR < 0) ? cmul(a, w) : cmulc(a, w);
+          const V w = __ldg(tw + ((tstep * q) & (NN - 1)));
+          a = (DIR < 0) ? VecOps<V>::mul(a, w) : VecOps<V>::mulc(a, w);
         }
         v[brev(q, ilog2(R))] = a;
       }
-      fft_dit<R, DIR>(v);
+      VecOps<V>::template fft<R, DIR>(v);
     }
     __syncthreads();   // every read of this round precedes every write
     if (on) {
 #pragma unroll
-      for (int q = 0; q < R; q++) zz[j0 + q * Ns] = v[q];
+      for (int q = 0; q < R; q++) zz[swz(j0 + q * Ns)] = v[q];
     }
     __syncthreads();
   }
 }
 
-template <int NN, int DIR>
-__device__ __forceinline__ void block_fft(float2* z, int nfft, const float2* __restrict__ tw, int tid) {
+template <int NN, int DIR, typename V>
+__device__ __forceinline__ void block_fft(V* z, int nfft, const V* __restrict__ tw, int tid) {
   if constexpr (NN == 4096) {
-    stockham_pass<NN, 16, DIR>(z, nfft, 1, tw, tid);
-    stockham_pass<NN, 16, DIR>(z, nfft, 16, tw, tid);
-    stockham_pass<NN, 16, DIR>(z, nfft, 256, tw, tid);
+    stockham_pass<NN, 16, DIR, V>(z, nfft, 1, tw, tid);
+    stockham_pass<NN, 16, DIR, V>(z, nfft, 16, tw, tid);
+    stockham_pass<NN, 16, DIR, V>(z, nfft, 256, tw, tid);
   } else if constexpr (NN == 2048) {
-    stockham_pass<NN, 16, DIR>(z, nfft, 1, tw, tid);
-    stockham_pass<NN, 16, DIR>(z, nfft, 16, tw, tid);
-    stockham_pass<NN, 8, DIR>(z, nfft, 256, tw, tid);
+    stockham_pass<NN, 16, DIR, V>(z, nfft, 1, tw, tid);
+    stockham_pass<NN, 16, DIR, V>(z, nfft, 16, tw, tid);
+    stockham_pass<NN, 8, DIR, V>(z, nfft, 256, tw, tid);
   } else if constexpr (NN == 1024) {
-    stockham_pass<NN, 16, DIR>(z, nfft, 1, tw, tid);
-    stockham_pass<NN, 8, DIR>(z, nfft, 16, tw, tid);
-    stockham_pass<NN, 8, DIR>(z, nfft, 128, tw, tid);
+    stockham_pass<NN, 16, DIR, V>(z, nfft, 1, tw, tid);
+    stockham_pass<NN, 8, DIR, V>(z, nfft, 16, tw, tid);
+    stockham_pass<NN, 8, DIR, V>(z, nfft, 128, tw, tid);
   } else {
     static_assert(NN == 512, "supported frame sizes: 512, 1024, 2048, 4096");
-    stockham_pass<NN, 8, DIR>(z, nfft, 1, tw, tid);
-    stockham_pass<NN, 8, DIR>(z, nfft, 8, tw, tid);
-    stockham_pass<NN, 8, DIR>(z, nfft, 64, tw, tid);
+    stockham_pass<NN, 8, DIR, V>(z, nfft, 1, tw, tid);
+    stockham_pass<NN, 8, DIR, V>(z, nfft, 8, tw, tid);
+    stockham_pass<NN, 8, DIR, V>(z, nfft, 64, tw, tid);
   }
 }
 
-// X_i[j] of frame f (0: t, 1: t+1) from the packed half-scaled spectrum Z = FFT(0.5*w*(x_t + i x_{t+1}))
+// X_i[j] of frame f from the packed half-scaled double spectrum Z = FFT(0.5*w*(x_t + i x_{t+1}))
 template <int NN>
-__device__ __forceinline__ float2 unpack_n(const float2* z, int l, int f) {
+__device__ __forceinline__ double2 unpack_nd(const double2* z, int l, int f) {
   constexpr int L = NN / 2 + 2;
   const int j = (l == L - 1) ? NN / 2 - 1 : l;   // pseudo-bin: conj of bin N/2-1 (SURVEY B-4)
-  const float2 a = z[j], b = z[(NN - j) & (NN - 1)];
-  float2 x;
-  if (f == 0) x = make_float2(a.x + b.x, a.y - b.y);
-  else x = make_float2(a.y + b.y, b.x - a.x);
+  const double2 a = z[swz(j)], b = z[swz((NN - j) & (NN - 1))];
+  double2 x;
+  if (f == 0) x = make_double2(a.x + b.x, a.y - b.y);
+  else x = make_double2(a.y + b.y, b.x - a.x);
   if (l == L - 1) x.y = -x.y;
   return x;
 }
@@ -111,33 +132,16 @@ __device__ __forceinline__ float wrap_diff_n(float a, float b) {   // phase.cpp:
   return d > 3.14159265358979f ? 6.28318530717959f - d : d;
 }
 
-// FP64 re-decision of one (bin, frame): exact double DFT of that bin for every microphone, one warp per item
+// Decision of one (bin, frame) in double from the double spectra (phase.cpp:89-123, phasempf.cpp:212-248)
 template <int NN>
-__device__ __forceinline__ unsigned phase_decide_fp64_n(const KernelParams& p, int s, int t, int l, int f, int lane, bool use_gate) {
-  constexpr int L = NN / 2 + 2, H = NN / 2;
-  const int j = (l == L - 1) ? NN / 2 + 1 : l;
+__device__ __forceinline__ unsigned phase_decide_d(const KernelParams& p, const double2* zall, int l, int f, bool use_gate) {
   double phi[BF_MAX_MICS_DEV];
   double magsum = 0.0;
   for (int ch = 0; ch < p.M; ch++) {
-    const int hf = t + f;
-    const float* h0 = (hf - 1 < 0) ? p.prev_hop + ((size_t)s * p.M + ch) * H
-                                   : p.in + (size_t)s * p.in_stream_stride + (size_t)ch * p.in_mic_stride + (size_t)(hf - 1) * H;
-    const float* h1 = p.in + (size_t)s * p.in_stream_stride + (size_t)ch * p.in_mic_stride + (size_t)hf * H;
-    double re = 0.0, im = 0.0;
-    for (int n = lane; n < NN; n += 32) {
-      const double xv = (double)(n < H ? h0[n] : h1[n - H]) * p.win_d[n];
-      const double2 w = p.twid_d[(int)(((long long)j * n) & (NN - 1))];
-      re = fma(xv, w.x, re);
-      im = fma(xv, w.y, im);
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      re += __shfl_xor_sync(0xffffffffu, re, o);
-      im += __shfl_xor_sync(0xffffffffu, im, o);
-    }
-    magsum += hypot(re, im);
+    const double2 x = unpack_nd<NN>(zall + (size_t)ch * NN, l, f);
+    magsum += hypot(x.x, x.y);
     const double2 w = p.steer_d[(size_t)l * p.M + ch];
-    phi[ch] = atan2(im * w.x - re * w.y, re * w.x + im * w.y);
+    phi[ch] = atan2(x.y * w.x - x.x * w.y, x.x * w.x + x.y * w.y);
   }
   unsigned fl = 0;
   if (!use_gate || (magsum / p.M) / (double)NN > p.mag_threshold_d) fl |= 1;
@@ -159,29 +163,25 @@ __device__ __forceinline__ unsigned phase_decide_fp64_n(const KernelParams& p, i
 
 // phase.cpp:70-134 / phasempf.cpp:193-302 for the two frames of a pair -> sc.y
 template <int ALGO, int NN>
-__device__ __forceinline__ void phase_pair_n(const KernelParams& p, int s, int t, bool two, const float2* zall, GenScratch<NN>& sc,
+__device__ __forceinline__ void phase_pair_n(const KernelParams& p, int s, int t, bool two, const double2* zall, GenScratch<NN>& sc,
                                              int& cur_L, int& first_L, int tid) {
   constexpr int L = NN / 2 + 2;
   const int M = p.M, nf = two ? 2 : 1;
-  const int lane = tid & 31, warp = tid >> 5;
   constexpr bool kGate = (ALGO == ALGO_PHASE);
   const int npairs = M * (M - 1) / 2;
-  // ---- decisions (FP32, guard band -> FP64 recheck list) ----
+  // ---- decisions: FP32 trigonometry on the double spectra; results within rounding of a threshold redone in double ----
   for (int l = tid; l < L; l += kGenThreads) {
     for (int f = 0; f < nf; f++) {
       if (l == 0) { sc.flag[f][l] = 0; continue; }
-      float magsum = 0.f, guard = 0.f, esum = 0.f;
+      float magsum = 0.f;
       float phi[BF_MAX_MICS_DEV];
       const float2* st = p.steer + (size_t)l * p.C * M;
       for (int ch = 0; ch < M; ch++) {
-        const float2 x = unpack_n<NN>(zall + (size_t)ch * NN, l, f);
+        const double2 xd = unpack_nd<NN>(zall + (size_t)ch * NN, l, f);
+        const float2 x = make_float2((float)xd.x, (float)xd.y);
         const float2 w = st[ch];
-        const float a = sqrtf(fmaf(x.x, x.x, x.y * x.y));
-        magsum += a;
+        magsum += sqrtf(fmaf(x.x, x.x, x.y * x.y));
         phi[ch] = atan2f(x.y * w.x - x.x * w.y, x.x * w.x + x.y * w.y);   // arg(conj(w) x)
-        const float e = sc.sqrtE[f][ch];
-        esum += e;
-        guard += fminf(3.2f, 4.0e-6f * e / fmaxf(a, 1e-30f) + 2.0e-6f);
       }
       float tot = 0.f;
       for (int a = M - 2; a >= 0; a--) {
@@ -189,30 +189,23 @@ __device__ __forceinline__ void phase_pair_n(const KernelParams& p, int s, int t
         for (int b = a + 1; b < M; b++) lvl += wrap_diff_n(phi[a], phi[b]);
         tot = lvl + tot;
       }
-      const float mean_diff = npairs > 0 ? tot / (float)npairs : __int_as_float(0x7fc00000);
-      guard *= 2.0f / (float)M;
+      const float mean_diff = npairs > 0 ? tot / (float)npairs : __int_as_float(0x7fc00000);   // M = 1: 0/0 (phase.cpp:111)
       unsigned fl = 0;
-      bool doubt = false;
+      bool doubt = fabsf(mean_diff - p.min_phase_rad) <= 4.0e-6f;   // float steering table + atan2f: ~1e-6 rad
       const float thr = p.thr_phase_mag;
       if (kGate) {
         if (magsum > thr) fl |= 1;
-        if (fabsf(magsum - thr) <= 2.0e-5f * esum + 1.0e-6f * thr) doubt = true;
+        if (fabsf(magsum - thr) <= 2.0e-6f * thr) doubt = true;
       } else {
         fl |= 1;
       }
       if (mean_diff < p.min_phase_rad) fl |= 2;
-      if (fabsf(mean_diff - p.min_phase_rad) <= guard && magsum > 1.0e-4f * esum) doubt = true;
-      if (doubt && p.win_d != nullptr) sc.recheck[atomicAdd(&sc.n_recheck, 1)] = (unsigned short)(l * 2 + f);
+      if (doubt && M > 1) fl = phase_decide_d<NN>(p, zall, l, f, kGate);
       sc.flag[f][l] = (unsigned char)fl;
     }
   }
   __syncthreads();
-  for (int q = warp; q < sc.n_recheck; q += kGenThreads / 32) {
-    const int l = sc.recheck[q] >> 1, f = sc.recheck[q] & 1;
-    const unsigned fl = phase_decide_fp64_n<NN>(p, s, t, l, f, lane, kGate);
-    if (lane == 0) sc.flag[f][l] = (unsigned char)fl;
-  }
-  __syncthreads();
+  (void)s; (void)t;
   // ---- per-bin output; phasempf: MCRA + bi-channel post-filter, state in global memory ([7][L], bin fastest) ----
   int cl = cur_L, fst = first_L;
   float* stg = (ALGO == ALGO_PHASEMPF) ? p.mpf_state + (size_t)s * 7 * L : nullptr;
@@ -226,20 +219,22 @@ __device__ __forceinline__ void phase_pair_n(const KernelParams& p, int s, int t
     for (int l = tid; l < L; l += kGenThreads) {
       float2 y = make_float2(0.f, 0.f);
       if (l == 0) {
-        if (ALGO == ALGO_PHASE) y = unpack_n<NN>(zall, 0, f);   // phase.cpp:87; phasempf leaves bin 0 at 0 (SURVEY B-5)
+        if (ALGO == ALGO_PHASE) { const double2 xd = unpack_nd<NN>(zall, 0, f); y = make_float2((float)xd.x, (float)xd.y); }   // phase.cpp:87; phasempf leaves bin 0 at 0 (B-5)
         sc.y[f][l] = y;
         continue;
       }
       float magsum = 0.f;
       float2 x0 = make_float2(0.f, 0.f);
       for (int ch = 0; ch < M; ch++) {
-        const float2 x = unpack_n<NN>(zall + (size_t)ch * NN, l, f);
+        const double2 xd = unpack_nd<NN>(zall + (size_t)ch * NN, l, f);
+        const float2 x = make_float2((float)xd.x, (float)xd.y);
         if (ch == 0) x0 = x;
         magsum += sqrtf(fmaf(x.x, x.x, x.y * x.y));
       }
       const float mag_mean = magsum / (float)M;
-      const float a0 = sqrtf(fmaf(x0.x, x0.x, x0.y * x0.y));
-      const float2 unit = a0 > 0.f ? make_float2(x0.x / a0, x0.y / a0) : make_float2(1.f, 0.f);   // e^{i arg X_0}
+      const float n0 = fmaf(x0.x, x0.x, x0.y * x0.y);
+      const float r0 = rsqrtf(n0);
+      const float2 unit = n0 > 0.f ? make_float2(x0.x * r0, x0.y * r0) : make_float2(1.f, 0.f);   // e^{i arg X_0}
       const unsigned fl = sc.flag[f][l];
       if (ALGO == ALGO_PHASE) {
         const float mag = ((fl & 1) && (fl & 2)) ? mag_mean : mag_mean * p.mag_mult;   // phase.cpp:114-123
@@ -286,13 +281,14 @@ __device__ __forceinline__ void phase_pair_n(const KernelParams& p, int s, int t
 template <int ALGO, int NN>
 __global__ void __launch_bounds__(kGenThreads, 1) frames_kernel_n(const KernelParams p) {
   constexpr int H = NN / 2, L = NN / 2 + 2;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  float2* zall = reinterpret_cast<float2*>(smem_raw);          // [M][NN]
-  float2* gbuf = zall + (size_t)p.M * NN;                       // [NN]
-  GenScratch<NN>& sc = *reinterpret_cast<GenScratch<NN>*>(gbuf + NN);
   constexpr bool kPha = (ALGO == ALGO_PHASE || ALGO == ALGO_PHASEMPF);
   constexpr bool kSmooth = (ALGO == ALGO_PHASEMPF);
-  const int tid = threadIdx.x, lane = tid & 31;
+  typedef typename std::conditional<kPha, double2, float2>::type ZV;   // forward spectra: double for the phase masks
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  ZV* zall = reinterpret_cast<ZV*>(smem_raw);                            // [M][NN]
+  float2* gbuf = reinterpret_cast<float2*>(zall + (size_t)p.M * NN);     // [NN]
+  GenScratch<NN>& sc = *reinterpret_cast<GenScratch<NN>*>(gbuf + NN);
+  const int tid = threadIdx.x;
   const int M = p.M;
   const int s = blockIdx.x + p.stream_begin;
   const float2* tw = p.twid_f;
@@ -309,46 +305,52 @@ __global__ void __launch_bounds__(kGenThreads, 1) frames_kernel_n(const KernelPa
   for (int ip = 0; ip < npairs; ip++) {
     const int t = p.hop_begin + 2 * ip;
     const bool two = t + 1 < p.hop_end;
-    if (tid < 2 * BF_MAX_MICS_DEV) (&sc.esum[0][0])[tid] = 0.f;
-    if (tid == 0) sc.n_recheck = 0;
-    __syncthreads();
     // ---- window + pack: z = 0.5*w*(frame_t + i*frame_{t+1}), frame_t = [hop t-1 | hop t] (util.h:217-242) ----
     for (int ch = 0; ch < M; ch++) {
       const float* base = p.in + (size_t)s * p.in_stream_stride + (size_t)ch * p.in_mic_stride;
       const float* ha = (t - 1 < 0) ? p.prev_hop + ((size_t)s * M + ch) * H : base + (size_t)(t - 1) * H;
       const float* hb = base + (size_t)t * H;
       const float* hc = two ? base + (size_t)(t + 1) * H : hb;
-      float e0 = 0.f, e1 = 0.f;
-      for (int n = tid; n < NN; n += kGenThreads) {
-        const float w = 0.5f * __ldg(win + n);
-        const float ft = (n < H) ? __ldg(ha + n) : __ldg(hb + n - H);
-        const float ft1 = !two ? 0.f : ((n < H) ? __ldg(hb + n) : __ldg(hc + n - H));
-        const float2 z = make_float2(ft * w, ft1 * w);
-        zall[(size_t)ch * NN + n] = z;
-        e0 = fmaf(z.x, z.x, e0);
-        e1 = fmaf(z.y, z.y, e1);
-      }
-      if (kPha) {
+      // first half of the frames: (hop t-1, hop t); second half: (hop t, hop t+1); loads of a half are issued together
+      constexpr int kIter = H / kGenThreads;
+      float fa[kIter], fb[kIter], fc[kIter];
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) { e0 += __shfl_xor_sync(0xffffffffu, e0, o); e1 += __shfl_xor_sync(0xffffffffu, e1, o); }
-        if (lane == 0) { atomicAdd(&sc.esum[0][ch], e0); atomicAdd(&sc.esum[1][ch], e1); }
+      for (int k = 0; k < kIter; k++) {
+        const int n = tid + k * kGenThreads;
+        fa[k] = __ldg(ha + n);
+        fb[k] = __ldg(hb + n);
+        fc[k] = two ? __ldg(hc + n) : 0.f;
+      }
+#pragma unroll
+      for (int k = 0; k < kIter; k++) {
+        const int n = tid + k * kGenThreads;
+        const float b1 = two ? fb[k] : 0.f;
+        if constexpr (kPha) {
+          const double w0 = 0.5 * p.win_d[n], w1 = 0.5 * p.win_d[n + H];
+          zall[(size_t)ch * NN + swz(n)] = make_double2((double)fa[k] * w0, (double)b1 * w0);
+          zall[(size_t)ch * NN + swz(n + H)] = make_double2((double)fb[k] * w1, (double)fc[k] * w1);
+        } else {
+          const float w0 = 0.5f * __ldg(win + n), w1 = 0.5f * __ldg(win + n + H);
+          zall[(size_t)ch * NN + swz(n)] = make_float2(fa[k] * w0, b1 * w0);
+          zall[(size_t)ch * NN + swz(n + H)] = make_float2(fb[k] * w1, fc[k] * w1);
+        }
       }
     }
     __syncthreads();
-    if (kPha && tid < M) { sc.sqrtE[0][tid] = 2.0f * sqrtf(sc.esum[0][tid]); sc.sqrtE[1][tid] = 2.0f * sqrtf(sc.esum[1][tid]); }
-    block_fft<NN, -1>(zall, M, tw, tid);   // begins and ends with block barriers
+    if constexpr (kPha) block_fft<NN, -1, double2>(zall, M, p.twid_d, tid);
+    else block_fft<NN, -1, float2>(zall, M, tw, tid);
     // ---- per-bin beamformer ----
-    if (ALGO == ALGO_DAS) {
+    if constexpr (ALGO == ALGO_DAS) {
       // das.cpp:60-63 commutes with the frame packing: G[j] = sum_i ceff_i[j] * Z_i[j] over all N bins
       for (int j = tid; j < NN; j += kGenThreads) {
         float2 acc = make_float2(0.f, 0.f);
         for (int ch = 0; ch < M; ch++) {
-          const float2 z = zall[(size_t)ch * NN + j];
+          const float2 z = zall[(size_t)ch * NN + swz(j)];
           const float2 w = __ldg(p.das_ceff + (size_t)ch * NN + j);
           acc.x = fmaf(z.x, w.x, acc.x); acc.x = fmaf(-z.y, w.y, acc.x);
           acc.y = fmaf(z.x, w.y, acc.y); acc.y = fmaf(z.y, w.x, acc.y);
         }
-        gbuf[j] = make_float2(2.0f * acc.x, 2.0f * acc.y);
+        gbuf[swz(j)] = make_float2(2.0f * acc.x, 2.0f * acc.y);
       }
     } else {
       phase_pair_n<ALGO, NN>(p, s, t, two, zall, sc, cur_L, first_L, tid);
@@ -360,8 +362,8 @@ __global__ void __launch_bounds__(kGenThreads, 1) frames_kernel_n(const KernelPa
           y1 = make_float2(0.5f * (y1.x + p1.x), 0.5f * (y1.y - p1.y));
         }
         if (l == 0 || l == H) { y0.y = 0.f; y1.y = 0.f; }
-        gbuf[l] = make_float2(y0.x - y1.y, y0.y + y1.x);
-        if (l > 0 && l < H) gbuf[NN - l] = make_float2(y0.x + y1.y, y1.x - y0.y);
+        gbuf[swz(l)] = make_float2(y0.x - y1.y, y0.y + y1.x);
+        if (l > 0 && l < H) gbuf[swz(NN - l)] = make_float2(y0.x + y1.y, y1.x - y0.y);
       }
       if (p.capture) {
         for (int l = tid; l < L; l += kGenThreads)
@@ -379,13 +381,13 @@ __global__ void __launch_bounds__(kGenThreads, 1) frames_kernel_n(const KernelPa
       }
     }
     __syncthreads();
-    block_fft<NN, 1>(gbuf, 1, tw, tid);
+    block_fft<NN, 1, float2>(gbuf, 1, tw, tid);
     // ---- synthesis window, overlap-add (util.h:244-253, 301-302), optional smoother ----
     float* o0 = p.out + (size_t)s * p.out_stream_stride + (size_t)t * H;
     const int S1 = kSmooth ? p.smooth_size - 1 : 0;
     for (int n = tid; n < H; n += kGenThreads) {
       const float w0 = __ldg(win + n) * p.out_scale, w1 = __ldg(win + n + H) * p.out_scale;
-      const float2 a = gbuf[n], b = gbuf[n + H];
+      const float2 a = gbuf[swz(n)], b = gbuf[swz(n + H)];
       const float r0 = sc.tail[n] + a.x * w0;
       if (kSmooth) sc.ola[S1 + n] = r0; else o0[n] = r0;
       if (two) {
@@ -420,21 +422,22 @@ __global__ void __launch_bounds__(kGenThreads, 1) frames_kernel_n(const KernelPa
 }
 
 template <int NN>
-static size_t gen_smem(int M) { return sizeof(float2) * ((size_t)M * NN + NN) + sizeof(GenScratch<NN>) + 16; }
+static size_t gen_smem(int M, bool pha) { return (pha ? sizeof(double2) : sizeof(float2)) * (size_t)M * NN + sizeof(float2) * NN + sizeof(GenScratch<NN>) + 16; }
 
-size_t frames_kernel_n_smem(int N, int M) {
+size_t frames_kernel_n_smem(int N, int M, int algo) {
+  const bool pha = algo == ALGO_PHASE || algo == ALGO_PHASEMPF;
   switch (N) {
-    case 512: return gen_smem<512>(M);
-    case 1024: return gen_smem<1024>(M);
-    case 2048: return gen_smem<2048>(M);
-    case 4096: return gen_smem<4096>(M);
+    case 512: return gen_smem<512>(M, pha);
+    case 1024: return gen_smem<1024>(M, pha);
+    case 2048: return gen_smem<2048>(M, pha);
+    case 4096: return gen_smem<4096>(M, pha);
   }
   return ~(size_t)0;
 }
 
 template <int ALGO, int NN>
 static cudaError_t launch_n(const KernelParams& p, cudaStream_t st) {
-  const size_t smem = gen_smem<NN>(p.M);
+  const size_t smem = gen_smem<NN>(p.M, ALGO == ALGO_PHASE || ALGO == ALGO_PHASEMPF);
   cudaError_t e = cudaFuncSetAttribute(frames_kernel_n<ALGO, NN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   frames_kernel_n<ALGO, NN><<<p.n_streams, kGenThreads, smem, st>>>(p);

@@ -44,6 +44,9 @@ WORKLOADS = {
                 interferers=(80.0, -60.0, 150.0), kernel="sel_pairs_kernel<gss>"),
     "c4": dict(name="C4: PhaseMPF 2-mic (binaural) 4096-pt, phase mask + MCRA bi-channel post-filter", algo="phasempf", mics="binaural",
                n_streams=1184, hops_per_step=47, hop=2048, interferers=(), kernel="frames_kernel_n<phasempf,4096>"),
+    # BASELINE.json configs[4]: steered-response sweep; streams are sharded across ranks and the maps are gathered (NCCL)
+    "c5": dict(name="C5: 64-mic (8x8 grid, 4 cm) steered-response DAS sweep over 360 directions, 1024-pt", algo="das", mics="grid64",
+               n_streams=8, hops_per_step=188, interferers=(), kernel="srp_power_kernel", srp_dirs=360),
     "ph": dict(name="Phase 3-mic (aira3) 1024-pt phase mask", algo="phase", mics="aira3", n_streams=1184, hops_per_step=188,
                interferers=(), kernel="frames_kernel_1024<phase>"),
 }
@@ -153,6 +156,120 @@ def cpu_sample(cfg, algo, mic_xy, cores, seed, hop=H, target_s=15.0):
     return v, dt, "%d streams x %d hops (%.1f s audio) of the same workload, %d threads, %.1f s wall" % (nstr, hops, nstr * hops * hop / SR, cores, dt)
 
 
+def run_srp(args, wl, bf, rank, local_rank, world, cores):
+    """C5: steered-response maps [B][T][360]; a step = one sweep over the rank's streams + the gather of all maps."""
+    import torch
+    import torch.distributed as dist
+    from beamform_b200.shard import gather_maps
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    mic_xy = bf.GEOMETRIES[wl["mics"]]
+    M, B, T, D = len(mic_xy), wl["n_streams"], wl["hops_per_step"], wl["srp_dirs"]
+    L = T * H
+    thetas = (-180.0 + 360.0 * np.arange(D) / D).astype(np.float32)
+    cfg = bf.make_config("das", mics=wl["mics"], device=local_rank)
+    beam = bf.Beamformer(cfg, n_streams=B)
+    x = device_synth(torch, mic_xy, B, L, seed=0xBEA4F0 + 1000 * rank, device=dev)
+    maps = torch.empty((B, T, D), dtype=torch.float32, device=dev)
+    stream = torch.cuda.current_stream()
+
+    def step():
+        beam.srp_device(x.data_ptr(), thetas, maps.data_ptr(), T, stream_ptr=stream.cuda_stream)
+        return gather_maps(maps, world * B) if world > 1 else maps
+
+    def fence():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    fence()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    l0 = beam.kernel_launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        allm = step()
+    e1.record(stream)
+    fence()
+    clocks = sampler.stop()
+    t_max = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t_max, op=dist.ReduceOp.MAX)
+    elapsed_ms = float(t_max.item())
+    launches = beam.kernel_launches - l0
+    value = world * B * L / SR * args.steps / (elapsed_ms * 1e-3)
+    e2e = None
+    if not args.no_e2e:
+        xh = torch.empty((B, M, L), dtype=torch.float32, pin_memory=True)
+        xh.copy_(x)
+        mh = torch.empty((B, T, D), dtype=torch.float32, pin_memory=True)
+        xd = torch.empty_like(x)
+
+        def e2e_step():
+            xd.copy_(xh, non_blocking=True)
+            beam.srp_device(xd.data_ptr(), thetas, maps.data_ptr(), T, stream_ptr=stream.cuda_stream)
+            mh.copy_(maps, non_blocking=True)
+            torch.cuda.synchronize()
+
+        e2e_step()
+        fence()
+        n_e2e = max(1, min(args.steps, 3))
+        t0 = time.perf_counter()
+        for _ in range(n_e2e):
+            e2e_step()
+        dt = time.perf_counter() - t0
+        t_e = torch.tensor([dt], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
+        e2e = {"value": world * B * L / SR * n_e2e / float(t_e.item()), "unit": "audio-s/s", "h2d_bytes_per_step": B * M * L * 4,
+               "d2h_bytes_per_step": B * T * D * 4, "steps": n_e2e, "checksum": float(mh.double().sum())}
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
+        flops = 8.0 * D * M * 513 * B * T          # SURVEY.md section 8d: 8*D*M*(N/2+1) per frame
+        ms_per_launch = elapsed_ms / args.steps
+        achieved = flops / (ms_per_launch * 1e-3) / 1e12
+        cpu = None
+        if not args.no_cpu and world == 1:
+            from beamform_b200.synth import synth_batch
+            from oracle_lib import Oracle
+            nfr = 2
+            xs = synth_batch(mic_xy, cores, nfr * H, seed=9)
+            t0 = time.perf_counter()
+            with ThreadPoolExecutor(max_workers=cores) as ex:
+                list(ex.map(lambda b: Oracle(cfg).srp(xs[b], thetas.astype(np.float64)), range(cores)))
+            dt = time.perf_counter() - t0
+            cpu = {"value": cores * nfr * H / SR / dt, "unit": "audio-s/s", "cores": cores, "kind": "port",
+                   "sample": "%d streams x %d frames of the same sweep (oracle: reference DAS formula per direction), %d threads, %.1f s wall" % (cores, nfr, cores, dt)}
+        print(json.dumps({
+            "metric": "beamformed audio-sec/sec", "value": value, "unit": "audio-s/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_launch, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": wl["name"], "algo": "srp", "n_mics": M, "fft_win": 2 * H, "hop": H, "sample_rate": SR, "directions": D,
+                       "streams_per_gpu": B, "hops_per_step": T, "audio_s_per_step_per_gpu": B * L / SR,
+                       "l2_policy": "spectra workspace (%d MB) larger than L2, no flush" % (514 * B * T * M * 8 // 2 ** 20),
+                       "collective": "all_gather of maps (NCCL)" if world > 1 else "none"},
+            "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+                         "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (of measured)" if peaks else "fallback 1400",
+                         "kernel": "srp_power_kernel (+ srp_spectra_kernel, ~2 % of the step)", "kernel_ms_per_launch": ms_per_launch,
+                         "algorithmic_flops_per_launch": flops,
+                         "note": "round 1 runs the contraction on the FP32 pipes (no tensor instructions yet); the tensor peak is the honest denominator"},
+            "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks}))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -184,6 +301,8 @@ def main():
               "streams_per_gpu": B, "hops_per_step": T, "audio_s_per_step_per_gpu": B * T * H / SR,
               "input_bytes_per_step_per_gpu": B * M * T * H * 4, "l2_policy": "inputs larger than L2 (126 MB), no flush"}
 
+    if "srp_dirs" in wl and args.impl != "reference":
+        return run_srp(args, wl, bf, rank, local_rank, world, cores)
     if args.impl == "reference":
         if rank != 0:
             return 0
