@@ -8,8 +8,10 @@
 //   srp_power_kernel    per bin l a complex GEMM  Y_l[d][f] = A_l[d][i] X_l[i][f]  (A_l generated on the fly from the
 //                       delay table, exact phase reduction in double), |Y|^2 weighted by the bin's multiplicity
 //                       (mirror bins share |y|, SURVEY B-3/B-4 pair excepted) and accumulated over l in registers.
-// This round's power kernel runs the contraction on the FP32 pipes (64x64x64 shared-memory tiles, 4x4 register
-// tiles); moving it to tcgen05 with a BF16x3 split is the next step.
+// The product path runs the contraction on tcgen05 (srp_tc_kernel.cu, BF16x3 split, TMEM accumulators); the FP32-pipe
+// version below (64x64x64 shared-memory tiles, 4x4 register tiles) is kept as an A/B cross-check (env BF_SRP_FP32).
+#include <cstdlib>
+
 #include "bf_device.h"
 #include "fft_reg.cuh"
 #include "warp_fft1024.cuh"
@@ -177,6 +179,9 @@ __global__ void __launch_bounds__(256, 2) srp_power_kernel(const float2* __restr
     }
 }
 
+cudaError_t launch_srp_power_tc(const float2* xs, const double* tau, const double* freqs_l, float* maps, int D, int M, long long F,
+                                cudaStream_t st);
+
 cudaError_t launch_srp(const KernelParams& p, float2* xs, const double* tau, const double* freqs_l, float* maps, int D, int n_hops,
                        cudaStream_t st) {
   const size_t smem1 = sizeof(float2) * (1024 + 8 * 1024);
@@ -187,6 +192,7 @@ cudaError_t launch_srp(const KernelParams& p, float2* xs, const double* tau, con
   e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   const long long F = (long long)p.n_streams * n_hops;
+  if (!getenv("BF_SRP_FP32")) return launch_srp_power_tc(xs, tau, freqs_l, maps, D, p.M, F, st);   // tensor-core path (default)
   const size_t smem2 = sizeof(float2) * 2 * 64 * kPad;
   e = cudaFuncSetAttribute(srp_power_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
   if (e != cudaSuccess) return e;
