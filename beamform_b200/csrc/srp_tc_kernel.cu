@@ -29,7 +29,6 @@ constexpr int kTcM = 128;                 // frames per CTA (UMMA M)
 constexpr int kTcD = 120;                 // directions per CTA
 constexpr int kTcN = 2 * kTcD;            // UMMA N
 constexpr int kTcK = 128;                 // 2 * 64 microphones
-constexpr int kTcMics = 64;
 constexpr int kLboA = (kTcM / 8) * 128 + 16;   // bytes between K-cores (padded)
 constexpr int kLboB = (kTcN / 8) * 128 + 16;
 constexpr int kTileA = (kTcK / 8) * kLboA;      // bytes per A tile (hi or lo)
@@ -135,36 +134,56 @@ __global__ void __launch_bounds__(256, 1) srp_power_tc_kernel(const float2* __re
   const int dsub = (warp >> 2) * 60;                                  // this warp's directions: dsub .. dsub+59
   const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;       // this warp's quarter of the TMEM lanes (= frames)
 
-  for (int l = 0; l < kSrpBins; l++) {
-    // ---- A operand: spectra of 128 frames, [Xr | Xi], bf16 hi/lo (coalesced 16-byte reads: two microphones each) ----
-    for (int c = tid; c < kTcM * (kTcMics / 2); c += 256) {
-      const int m = c >> 5, i = (c & 31) * 2;
+  // this thread's 16 spectra chunks (frame m, microphones i, i+1) and 15 steering items (direction d, microphones i, i+1)
+  // keep their delays in registers; the spectra of the NEXT bin are prefetched into registers behind the UMMAs
+  double tau_r[15][2];
+#pragma unroll
+  for (int q = 0; q < 15; q++) {
+    const int c = tid + 256 * q, d = c >> 5, i = (c & 31) * 2;
+#pragma unroll
+    for (int u = 0; u < 2; u++) tau_r[q][u] = (dbase + d < D && i + u < M) ? tau[(size_t)(dbase + d) * M + i + u] : 0.0;
+  }
+  float4 xr[16];
+  auto load_xs = [&](int l) {
+#pragma unroll
+    for (int q = 0; q < 16; q++) {
+      const int c = tid + 256 * q, m = c >> 5, i = (c & 31) * 2;
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
       if (fbase + m < F && i < M) {
         const float2* src = xs + ((size_t)l * F + fbase + m) * M + i;
-        const float2 x0 = src[0];
+        const float2 x0 = __ldg(src);
         v.x = x0.x; v.y = x0.y;
-        if (i + 1 < M) { const float2 x1 = src[1]; v.z = x1.x; v.w = x1.y; }
+        if (i + 1 < M) { const float2 x1 = __ldg(src + 1); v.z = x1.x; v.w = x1.y; }
       }
-      split_store2(a_hi, a_lo, tile_off(m, i, kLboA), v.x, v.z);            // Xr[i], Xr[i+1]
-      split_store2(a_hi, a_lo, tile_off(m, 64 + i, kLboA), v.y, v.w);       // Xi[i], Xi[i+1]
+      xr[q] = v;
     }
-    // ---- B operand: steering A_l[d][i] = exp(+i 2 pi f_l tau_{d,i}) / M (conj of das.cpp:41), two microphones per step ----
-    const double fl = freqs_l[l];
-    for (int c = tid; c < kTcD * (kTcMics / 2); c += 256) {
-      const int d = c >> 5, i = (c & 31) * 2;
-      float ar[2] = {0.f, 0.f}, ai[2] = {0.f, 0.f};
-      if (dbase + d < D) {
+  };
+  load_xs(0);
+
+  for (int l = 0; l < kSrpBins; l++) {
+    // ---- A operand: spectra of 128 frames, [Xr | Xi], bf16 hi/lo ----
 #pragma unroll
-        for (int u = 0; u < 2; u++)
-          if (i + u < M) {
-            const double turns = fl * tau[(size_t)(dbase + d) * M + i + u];
-            const float fr = (float)(turns - rint(turns));
-            float sn, cs;
-            sincospif(2.0f * fr, &sn, &cs);
-            ar[u] = cs * invM;
-            ai[u] = sn * invM;
-          }
+    for (int q = 0; q < 16; q++) {
+      const int c = tid + 256 * q, m = c >> 5, i = (c & 31) * 2;
+      split_store2(a_hi, a_lo, tile_off(m, i, kLboA), xr[q].x, xr[q].z);            // Xr[i], Xr[i+1]
+      split_store2(a_hi, a_lo, tile_off(m, 64 + i, kLboA), xr[q].y, xr[q].w);       // Xi[i], Xi[i+1]
+    }
+    // ---- B operand: steering A_l[d][i] = exp(+i 2 pi f_l tau_{d,i}) / M (conj of das.cpp:41): the phase is reduced to
+    //      [-1/2, 1/2] turn in double, then MUFU sin/cos (abs. error ~1e-6, two orders below the 1e-4 budget) ----
+    const double fl = freqs_l[l];
+#pragma unroll
+    for (int q = 0; q < 15; q++) {
+      const int c = tid + 256 * q, d = c >> 5, i = (c & 31) * 2;
+      float ar[2], ai[2];
+#pragma unroll
+      for (int u = 0; u < 2; u++) {
+        const double turns = fl * tau_r[q][u];
+        const float ang = 6.283185307179586f * (float)(turns - rint(turns));
+        float sn, cs;
+        __sincosf(ang, &sn, &cs);
+        const bool on = dbase + d < D && i + u < M;
+        ar[u] = on ? cs * invM : 0.f;
+        ai[u] = on ? sn * invM : 0.f;
       }
       split_store2(b_hi, b_lo, tile_off(d, i, kLboB), ar[0], ar[1]);                // Re row: [ Ar | -Ai ]
       split_store2(b_hi, b_lo, tile_off(d, 64 + i, kLboB), -ai[0], -ai[1]);
@@ -187,6 +206,7 @@ __global__ void __launch_bounds__(256, 1) srp_power_tc_kernel(const float2* __re
       }
       asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
     }
+    if (l + 1 < kSrpBins) load_xs(l + 1);   // in flight behind the UMMAs and the epilogue
     mbar_wait_or_trap(bar, (uint32_t)(l & 1));
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     // ---- epilogue: |Y|^2 weighted by the bin's multiplicity (mirror bins share |y|; 0, N/2-1, N/2 and the pseudo-bin count once) ----

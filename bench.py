@@ -46,7 +46,7 @@ WORKLOADS = {
                n_streams=1184, hops_per_step=47, hop=2048, interferers=(), kernel="frames_kernel_n<phasempf,4096>"),
     # BASELINE.json configs[4]: steered-response sweep; streams are sharded across ranks and the maps are gathered (NCCL)
     "c5": dict(name="C5: 64-mic (8x8 grid, 4 cm) steered-response DAS sweep over 360 directions, 1024-pt", algo="das", mics="grid64",
-               n_streams=8, hops_per_step=188, interferers=(), kernel="srp_power_kernel", srp_dirs=360),
+               n_streams=100, hops_per_step=188, interferers=(), kernel="srp_power_tc_kernel", srp_dirs=360),
     "ph": dict(name="Phase 3-mic (aira3) 1024-pt phase mask", algo="phase", mics="aira3", n_streams=1184, hops_per_step=188,
                interferers=(), kernel="frames_kernel_1024<phase>"),
 }
@@ -261,9 +261,9 @@ def run_srp(args, wl, bf, rank, local_rank, world, cores):
                        "collective": "all_gather of maps (NCCL)" if world > 1 else "none"},
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
                          "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (of measured)" if peaks else "fallback 1400",
-                         "kernel": "srp_power_kernel (+ srp_spectra_kernel, ~2 % of the step)", "kernel_ms_per_launch": ms_per_launch,
+                         "kernel": "srp_power_tc_kernel (tcgen05 BF16x3) + srp_spectra_kernel", "kernel_ms_per_launch": ms_per_launch,
                          "algorithmic_flops_per_launch": flops,
-                         "note": "round 1 runs the contraction on the FP32 pipes (no tensor instructions yet); the tensor peak is the honest denominator"},
+                         "note": "algorithmic FLOPs (8*D*M*513 per frame); the BF16x3 split issues 3x as many tensor FLOPs (K padded 2*M -> 128)"},
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks}))
     if world > 1:
         dist.destroy_process_group()
