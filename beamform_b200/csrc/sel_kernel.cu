@@ -82,24 +82,22 @@ __device__ __forceinline__ void unpack2(const float2* z, int l, float2& x0, floa
 }
 
 // Covariance of the P frames before `frame` from the ring (mvdr.cpp:87, :239-243) and its Cholesky factor.
-// ring_l: this bin's column of the per-stream ring [D][M][Lsel]; first = ring slot of frame-P.
+// hs: the item's P history frames, staged into shared memory as [k][M] (oldest first) by cp.async.
 template <int MM, typename T>
-__device__ __forceinline__ void ring_cov_chol(const KernelParams& p, HermLower<MM, T>& A, T (&invd)[MM], const float2* ring_l, int first) {
+__device__ __forceinline__ void ring_cov_chol(const KernelParams& p, HermLower<MM, T>& A, T (&invd)[MM], const float2* hs) {
   typedef HermLower<MM, T> HL;
-  const int M = p.M, D = p.ring_depth;
+  const int M = p.M;
 #pragma unroll
   for (int i = 0; i < MM; i++) A.dg[i] = T(0);
 #pragma unroll
   for (int i = 0; i < MM * (MM - 1) / 2; i++) A.lo[i] = mk<T>(T(0), T(0));
-  int slot = first;
 #pragma unroll 2
   for (int k = 0; k < p.P; k++) {
-    const float2* src = ring_l + (size_t)slot * M * p.Lsel;   // [slot][mic][bin]: bin-fastest, coalesced across a warp
-    if (++slot == D) slot = 0;
+    const float2* src = hs + k * M;
     cplx<T> h[MM];
 #pragma unroll
     for (int i = 0; i < MM; i++) {
-      const float2 v = (i < M) ? src[(size_t)i * p.Lsel] : make_float2(0.f, 0.f);
+      const float2 v = (i < M) ? src[i] : make_float2(0.f, 0.f);
       h[i] = mk<T>((T)v.x, (T)v.y);
     }
 #pragma unroll
@@ -113,7 +111,6 @@ __device__ __forceinline__ void ring_cov_chol(const KernelParams& p, HermLower<M
       }
     }
   }
-  if (p.debug & 4) return;
 #pragma unroll
   for (int j = 0; j < MM; j++) {
     if (j < M) {
@@ -145,12 +142,11 @@ __device__ __forceinline__ void ring_cov_chol(const KernelParams& p, HermLower<M
 
 // mvdr.cpp:86-94 with R = L L^H: z = L^{-1} d, u = L^{-1} x, y = (z^H u) / (z^H z)
 template <int MM, typename T>
-__device__ __forceinline__ float2 mvdr_ring_item(const KernelParams& p, const float2* ring_l, int first, const float2 (&x)[MM],
+__device__ __forceinline__ float2 mvdr_ring_item(const KernelParams& p, const float2* hs, const float2 (&x)[MM],
                                                  const float2* steer_l) {
   HermLower<MM, T> A;
   T invd[MM];
-  ring_cov_chol<MM, T>(p, A, invd, ring_l, first);
-  if (p.debug & 8) return make_float2((float)A.dg[0], (float)A.lo[5].x);
+  ring_cov_chol<MM, T>(p, A, invd, hs);
   cplx<T> z[MM], u[MM];
 #pragma unroll
   for (int i = 0; i < MM; i++) {
@@ -168,11 +164,11 @@ __device__ __forceinline__ float2 mvdr_ring_item(const KernelParams& p, const fl
 // lcmv.cpp:111-119: W = R^{-1} C (C^H R^{-1} C)^{-1}, y = W(:,0)^H x.  V = L^{-1} C, u = L^{-1} x, G = V^H V, b = V^H u,
 // y = g^H b with G g = e_0.
 template <int MM, typename T>
-__device__ __forceinline__ float2 lcmv_ring_item(const KernelParams& p, const float2* ring_l, int first, const float2 (&x)[MM],
+__device__ __forceinline__ float2 lcmv_ring_item(const KernelParams& p, const float2* hs, const float2 (&x)[MM],
                                                  const float2* steer_l) {
   HermLower<MM, T> A;
   T invd[MM];
-  ring_cov_chol<MM, T>(p, A, invd, ring_l, first);
+  ring_cov_chol<MM, T>(p, A, invd, hs);
   const int C = p.C, M = p.M;
   cplx<T> u[MM];
 #pragma unroll
@@ -368,7 +364,7 @@ __global__ void __launch_bounds__(kSelThreads, ALGO == ALGO_LCMV ? 1 : 2) sel_pa
           }
           y0 = make_float2(0.01f * x0[0].x, 0.01f * x0[0].y);   // mvdr.cpp:96 (overwritten when selected)
           y1 = make_float2(0.01f * x1[0].x, 0.01f * x1[0].y);
-          if (ALGO != ALGO_GSS && !(p.debug & 2)) {   // mvdr.cpp:99-101: every in-band bin appends every frame
+          if (ALGO != ALGO_GSS) {   // mvdr.cpp:99-101: every in-band bin appends every frame
             float2* ring_l = p.hist + (size_t)s * D * M * p.Lsel + p.sel_slot[l];
             int fs = fr0;
 #pragma unroll
@@ -438,38 +434,63 @@ __global__ void __launch_bounds__(kSelThreads, ALGO == ALGO_LCMV ? 1 : 2) sel_pa
       });
     }
     // ------------------------------------------------------------------ B2: per-item solves
-    if (live) {
-      // items start on warp 0; the last warp (busy with the inverse) is reached only by large work lists
-      for (int q = tid; q < ((p.debug & 1) ? 0 : sc.n_items); q += kSelThreads) {
-        const int l = sc.items[q] >> 1, f = sc.items[q] & 1;
+    if (live && ALGO == ALGO_GSS) {
+      for (int q = tid; q < sc.n_items; q += kSelThreads) {
+        const int l = sc.items[q] >> 1;
         const int slot = p.sel_slot[l];
         const float2* steer_l = p.steer + (size_t)l * p.C * M;
-        if (ALGO == ALGO_GSS) {
-          float2* Wg = p.gss_w + (size_t)s * 8 * M * p.Lsel + slot;   // [B][8][M][Lsel]
-          for (int ff = 0; ff < nf; ff++) {
-            if (!sc.flag[ff][l]) continue;
-            float2 x[8];
-#pragma unroll
-            for (int ch = 0; ch < 8; ch++) {
-              float2 a, b;
-              if (ch < M) unpack2(ztiles + ch * 1024, l, a, b); else a = b = make_float2(0.f, 0.f);
-              x[ch] = ff ? b : a;
-            }
-            sc.y[ff][l] = gss_item(p, Wg, (size_t)p.Lsel, x, steer_l);
-          }
-        } else {
+        float2* Wg = p.gss_w + (size_t)s * 8 * M * p.Lsel + slot;   // [B][8][M][Lsel]
+        for (int ff = 0; ff < nf; ff++) {
+          if (!sc.flag[ff][l]) continue;
           float2 x[8];
 #pragma unroll
           for (int ch = 0; ch < 8; ch++) {
             float2 a, b;
             if (ch < M) unpack2(ztiles + ch * 1024, l, a, b); else a = b = make_float2(0.f, 0.f);
-            x[ch] = f ? b : a;
+            x[ch] = ff ? b : a;
           }
-          const float2* ring_l = p.hist + (size_t)s * D * M * p.Lsel + slot;
-          int first = fr0 + f - p.P;   // slot of frame (t+f) - P
-          first %= D; if (first < 0) first += D;
-          sc.y[f][l] = (ALGO == ALGO_MVDR) ? mvdr_ring_item<8, float>(p, ring_l, first, x, steer_l)
-                                           : lcmv_ring_item<8, double>(p, ring_l, first, x, steer_l);
+          sc.y[ff][l] = gss_item(p, Wg, (size_t)p.Lsel, x, steer_l);
+        }
+      }
+    }
+    if (live && ALGO != ALGO_GSS) {
+      // mvdr / lcmv.  The spectrum tiles are dead after B1 (the current frame is in the ring too), so they become the
+      // staging area of the work list: every item thread pulls its P history frames + its own frame out of the ring
+      // with cp.async (8-byte pieces, coalesced across neighbouring items) in ONE round trip instead of walking P
+      // dependent loads, then builds the covariance from shared memory.  Items beyond the staging capacity take
+      // further batches.
+      const int per_item = (p.P + 1) * M;
+      const int stride = per_item | 1;                      // odd pitch in float2: conflict-free 8-byte accesses
+      int nb = (kSelWarps * 1024) / stride;
+      if (nb > kSelThreads) nb = kSelThreads;
+      float2* stg = ztiles;
+      const int n_items = sc.n_items;
+      for (int base = 0; base < n_items; base += nb) {
+        if (base > 0) __syncthreads();                      // previous batch consumed
+        const int q = base + tid;
+        const bool on = tid < nb && q < n_items;
+        float2* hs = stg + (size_t)tid * stride;
+        int l = 0, f = 0;
+        if (on) {
+          l = sc.items[q] >> 1; f = sc.items[q] & 1;
+          const float2* ring_l = p.hist + (size_t)s * D * M * p.Lsel + p.sel_slot[l];
+          int slot = (fr0 + f - p.P) % D;                   // ring slot of frame (t+f) - P
+          if (slot < 0) slot += D;
+          for (int k = 0; k <= p.P; k++) {
+            const float2* src = ring_l + (size_t)slot * M * p.Lsel;
+            if (++slot == D) slot = 0;
+            for (int i = 0; i < M; i++)
+              asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(hs + k * M + i)), "l"(src + (size_t)i * p.Lsel) : "memory");
+          }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        if (on) {
+          float2 x[8];
+#pragma unroll
+          for (int ch = 0; ch < 8; ch++) x[ch] = (ch < M) ? hs[p.P * M + ch] : make_float2(0.f, 0.f);
+          const float2* steer_l = p.steer + (size_t)l * p.C * M;
+          sc.y[f][l] = (ALGO == ALGO_MVDR) ? mvdr_ring_item<8, float>(p, hs, x, steer_l) : lcmv_ring_item<8, double>(p, hs, x, steer_l);
         }
       }
     }
