@@ -17,6 +17,7 @@
 //       pair, which hides the one transform that has no peer inside the solves' slack
 //   B3  Hermitian assembly of G = Yh_t + i*Yh_{t+1} for the next inverse
 // Spectra never leave the SM except for the history ring the algorithm itself keeps (mvdr.cpp:99-101).
+#include <cstdio>
 #include <cstdlib>
 
 #include "async_copy.cuh"
@@ -64,6 +65,8 @@ struct SelShared {
   float tail[512];
   int nonfinite[2][2];   // [pair parity][frame]: the frame's spectrum holds inf/NaN (cold start, SURVEY B-10)
   uint64_t bars[kSelWarps];
+  short sel_slot[kL1K];  // copies of the per-bin tables (B1 would otherwise chain two global loads per bin)
+  unsigned char inband[kL1K];
 };
 
 __device__ __forceinline__ float sqrt_approx(float x) {   // MUFU.SQRT; its ~2 ulp error sits far inside the gate's guard band
@@ -81,25 +84,72 @@ __device__ __forceinline__ void unpack2(const float2* z, int l, float2& x0, floa
   if (l == kL1K - 1) { x0.y = -x0.y; x1.y = -x1.y; }
 }
 
-// Covariance of the P frames before `frame` from the ring (mvdr.cpp:87, :239-243) and its Cholesky factor.
-// hs: the item's P history frames, staged into shared memory as [k][M] (oldest first) by cp.async.
-template <int MM, typename T>
-__device__ __forceinline__ void ring_cov_chol(const KernelParams& p, HermLower<MM, T>& A, T (&invd)[MM], const float2* hs) {
+// 1/sqrt(d) for the Cholesky pivots: MUFU.RSQ + one Newton step in FP32 (the IEEE sqrt and divide sequences are
+// ~40 dependent instructions per pivot on the solve's critical path); d <= 0 / NaN still end non-finite (B-10).
+__device__ __forceinline__ float inv_sqrt(float d) {
+  const float r = rsqrtf(d);
+  return d > 0.f && d < 3.0e38f ? r * fmaf(-0.5f * d * r, r, 1.5f) : r;
+}
+__device__ __forceinline__ double inv_sqrt(double d) { return 1.0 / sqrt(d); }
+
+// Per-thread software pipeline over the item's P+1 ring frames (P history frames oldest first, then the item's own
+// frame): every thread owns kStageDepth frame slots of M float2 in the (idle) spectrum tiles and keeps that many
+// frames in flight with cp.async (8-byte pieces, coalesced across the neighbouring bins of a warp: the ring is
+// bin-fastest).  ALL 256 threads of the CTA can carry an item at once (staging whole histories capped a batch at
+// 92); the depth is chosen per batch from the number of items: a quiet pair (few items) keeps the whole history in
+// flight in one L2 round trip, a busy pair runs depth 3 (a frame is consumed two rank-1 updates after its request).
+template <int kStageDepth>
+struct RingPipe {
+  const float2* ring_l;   // &ring[slot 0][mic 0][this bin]
+  float2* my;             // this thread's staging slots
+  size_t mic_stride, slot_stride;
+  int M, D, P;
+  int next_k, next_ring, next_stage, read_stage;
+  __device__ __forceinline__ void issue() {   // request frame next_k (if any) and close one cp.async group either way
+    if (next_k <= P) {
+      const float2* src = ring_l + (size_t)next_ring * slot_stride;
+      float2* dst = my + next_stage * M;
+      for (int i = 0; i < M; i++)
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst + i)), "l"(src + (size_t)i * mic_stride) : "memory");
+      if (++next_ring == D) next_ring = 0;
+      if (++next_stage == kStageDepth) next_stage = 0;
+    }
+    next_k++;
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  }
+  __device__ __forceinline__ void start() {
+#pragma unroll
+    for (int d = 0; d < kStageDepth; d++) issue();
+  }
+  // the oldest requested frame, once it has landed
+  template <int MM>
+  __device__ __forceinline__ void take(float2 (&h)[MM]) {
+    asm volatile("cp.async.wait_group %0;" ::"n"(kStageDepth - 1) : "memory");
+    const float2* src = my + read_stage * M;
+#pragma unroll
+    for (int i = 0; i < MM; i++) h[i] = (i < M) ? src[i] : make_float2(0.f, 0.f);
+    if (++read_stage == kStageDepth) read_stage = 0;
+  }
+};
+
+// Covariance of the P frames before the item's frame (mvdr.cpp:87, :239-243), its Cholesky factor, and the item's
+// own frame x (the last stage of the pipeline).
+template <int MM, typename T, class Pipe>
+__device__ __forceinline__ void ring_cov_chol(const KernelParams& p, HermLower<MM, T>& A, T (&invd)[MM], Pipe& pipe, float2 (&x)[MM]) {
   typedef HermLower<MM, T> HL;
   const int M = p.M;
 #pragma unroll
   for (int i = 0; i < MM; i++) A.dg[i] = T(0);
 #pragma unroll
   for (int i = 0; i < MM * (MM - 1) / 2; i++) A.lo[i] = mk<T>(T(0), T(0));
-#pragma unroll 2
+  pipe.start();
+#pragma unroll 1
   for (int k = 0; k < p.P; k++) {
-    const float2* src = hs + k * M;
+    float2 hf[MM];
+    pipe.template take<MM>(hf);
     cplx<T> h[MM];
 #pragma unroll
-    for (int i = 0; i < MM; i++) {
-      const float2 v = (i < M) ? src[i] : make_float2(0.f, 0.f);
-      h[i] = mk<T>((T)v.x, (T)v.y);
-    }
+    for (int i = 0; i < MM; i++) h[i] = mk<T>((T)hf[i].x, (T)hf[i].y);
 #pragma unroll
     for (int i = 0; i < MM; i++) {
       A.dg[i] = fma_t<T>(h[i].x, h[i].x, fma_t<T>(h[i].y, h[i].y, A.dg[i]));
@@ -110,16 +160,17 @@ __device__ __forceinline__ void ring_cov_chol(const KernelParams& p, HermLower<M
         r.y = fma_t<T>(h[i].y, h[j].x, fma_t<T>(-h[i].x, h[j].y, r.y));
       }
     }
+    pipe.issue();   // into the slot just consumed
   }
+  pipe.template take<MM>(x);
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
 #pragma unroll
   for (int j = 0; j < MM; j++) {
     if (j < M) {
       T d = A.dg[j] * T(1.001);   // whiteR diagonal (mvdr.cpp:242)
 #pragma unroll
       for (int k = 0; k < j; k++) { const cplx<T> l = A.lo[HL::idx(j, k)]; d = fma_t<T>(-l.x, l.x, fma_t<T>(-l.y, l.y, d)); }
-      const T ljj = sqrt(d);
-      const T inv = T(1) / ljj;
-      A.dg[j] = ljj;
+      const T inv = inv_sqrt(d);
       invd[j] = inv;
 #pragma unroll
       for (int i = j + 1; i < MM; i++) {
@@ -141,12 +192,12 @@ __device__ __forceinline__ void ring_cov_chol(const KernelParams& p, HermLower<M
 }
 
 // mvdr.cpp:86-94 with R = L L^H: z = L^{-1} d, u = L^{-1} x, y = (z^H u) / (z^H z)
-template <int MM, typename T>
-__device__ __forceinline__ float2 mvdr_ring_item(const KernelParams& p, const float2* hs, const float2 (&x)[MM],
-                                                 const float2* steer_l) {
+template <int MM, typename T, class Pipe>
+__device__ __forceinline__ float2 mvdr_ring_item(const KernelParams& p, Pipe& pipe, const float2* steer_l) {
   HermLower<MM, T> A;
   T invd[MM];
-  ring_cov_chol<MM, T>(p, A, invd, hs);
+  float2 x[MM];
+  ring_cov_chol<MM, T>(p, A, invd, pipe, x);
   cplx<T> z[MM], u[MM];
 #pragma unroll
   for (int i = 0; i < MM; i++) {
@@ -154,8 +205,28 @@ __device__ __forceinline__ float2 mvdr_ring_item(const KernelParams& p, const fl
     z[i] = mk<T>((T)d.x, (T)d.y);
     u[i] = mk<T>((T)x[i].x, (T)x[i].y);
   }
-  fwd_solve<MM, T>(p, A, invd, z);
-  fwd_solve<MM, T>(p, A, invd, u);
+  {   // z <- L^{-1} z and u <- L^{-1} u in one sweep: the two substitutions are independent chains
+    typedef HermLower<MM, T> HL;
+#pragma unroll
+    for (int i = 0; i < MM; i++) {
+      if (i < p.M) {
+        cplx<T> az = z[i], au = u[i];
+#pragma unroll
+        for (int k = 0; k < i; k++) {
+          const cplx<T> l = A.lo[HL::idx(i, k)];
+          az.x = fma_t<T>(-l.x, z[k].x, fma_t<T>(l.y, z[k].y, az.x));
+          az.y = fma_t<T>(-l.x, z[k].y, fma_t<T>(-l.y, z[k].x, az.y));
+          au.x = fma_t<T>(-l.x, u[k].x, fma_t<T>(l.y, u[k].y, au.x));
+          au.y = fma_t<T>(-l.x, u[k].y, fma_t<T>(-l.y, u[k].x, au.y));
+        }
+        z[i] = mk<T>(az.x * invd[i], az.y * invd[i]);
+        u[i] = mk<T>(au.x * invd[i], au.y * invd[i]);
+      } else {
+        z[i] = mk<T>(T(0), T(0));
+        u[i] = mk<T>(T(0), T(0));
+      }
+    }
+  }
   const cplx<T> num = cdot_conj<MM, T>(z, u);
   const T den = cdot_conj<MM, T>(z, z).x;
   return make_float2((float)(num.x / den), (float)(num.y / den));
@@ -163,12 +234,12 @@ __device__ __forceinline__ float2 mvdr_ring_item(const KernelParams& p, const fl
 
 // lcmv.cpp:111-119: W = R^{-1} C (C^H R^{-1} C)^{-1}, y = W(:,0)^H x.  V = L^{-1} C, u = L^{-1} x, G = V^H V, b = V^H u,
 // y = g^H b with G g = e_0.
-template <int MM, typename T>
-__device__ __forceinline__ float2 lcmv_ring_item(const KernelParams& p, const float2* hs, const float2 (&x)[MM],
-                                                 const float2* steer_l) {
+template <int MM, typename T, class Pipe>
+__device__ __forceinline__ float2 lcmv_ring_item(const KernelParams& p, Pipe& pipe, const float2* steer_l) {
   HermLower<MM, T> A;
   T invd[MM];
-  ring_cov_chol<MM, T>(p, A, invd, hs);
+  float2 x[MM];
+  ring_cov_chol<MM, T>(p, A, invd, pipe, x);
   const int C = p.C, M = p.M;
   cplx<T> u[MM];
 #pragma unroll
@@ -257,6 +328,7 @@ __global__ void __launch_bounds__(kSelThreads, ALGO == ALGO_LCMV ? 1 : 2) sel_pa
     tw[i] = make_float2(cs, sn);
   }
   for (int i = tid; i < H; i += kSelThreads) sc.tail[i] = p.tail[(size_t)s * H + i];
+  for (int i = tid; i < kL1K; i += kSelThreads) { sc.sel_slot[i] = (short)p.sel_slot[i]; sc.inband[i] = p.inband[i]; }
   if (lane == 0) mbar_init(&sc.bars[warp], 1);
   mbar_fence_init();
   __syncthreads();
@@ -284,6 +356,14 @@ __global__ void __launch_bounds__(kSelThreads, ALGO == ALGO_LCMV ? 1 : 2) sel_pa
   };
   if (use_tma && npairs > 0) issue(p.hop_begin);
 
+#ifdef BF_PHASE_TIMERS   // nvcc -DBF_PHASE_TIMERS + env BF_DEBUG=1: per-phase cycle totals of CTA 0 (profiling builds only)
+  long long ph_clk[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  long long ph_t = clock64();
+  int ph_items = 0;
+#define BF_PHASE(i) do { if (p.debug == 1) { const long long n_ = clock64(); ph_clk[i] += n_ - ph_t; ph_t = n_; } } while (0)
+#else
+#define BF_PHASE(i) do { } while (0)
+#endif
   for (int ip = 0; ip <= npairs; ip++) {
     const int t = p.hop_begin + 2 * ip;
     const bool live = ip < npairs;
@@ -324,13 +404,15 @@ __global__ void __launch_bounds__(kSelThreads, ALGO == ALGO_LCMV ? 1 : 2) sel_pa
 #pragma unroll
       for (int k2 = 0; k2 < 32; k2++) myz[k2 * 32 + lane] = v[k2];
     }
+    BF_PHASE(0);
     if (tid == 0) { sc.n_items = 0; sc.n_recheck = 0; sc.nonfinite[ip & 1][0] = 0; sc.nonfinite[ip & 1][1] = 0; }
     __syncthreads();   // (a) Z complete; G of the previous pair complete
+    BF_PHASE(1);
     const int fr0 = (p.ring_slot0 + (t - p.hop_begin)) % D;   // ring slot of frame t
     // ------------------------------------------------------------------ B1: gate, history append, defaults
     if (live) {
       for (int l = tid; l < kL1K; l += kSelThreads) {
-        const bool inb = p.inband[l] != 0 && !(ALGO == ALGO_MVDR && l == 0);
+        const bool inb = sc.inband[l] != 0 && !(ALGO == ALGO_MVDR && l == 0);
         float2 x0[8], x1[8];
         float st0 = 0.f, st1 = 0.f;
         if (!inb) {   // out of band: output 0 (mvdr.cpp:103), except mvdr's bin 0 which passes microphone 0 through
@@ -365,7 +447,7 @@ __global__ void __launch_bounds__(kSelThreads, ALGO == ALGO_LCMV ? 1 : 2) sel_pa
           y0 = make_float2(0.01f * x0[0].x, 0.01f * x0[0].y);   // mvdr.cpp:96 (overwritten when selected)
           y1 = make_float2(0.01f * x1[0].x, 0.01f * x1[0].y);
           if (ALGO != ALGO_GSS) {   // mvdr.cpp:99-101: every in-band bin appends every frame
-            float2* ring_l = p.hist + (size_t)s * D * M * p.Lsel + p.sel_slot[l];
+            float2* ring_l = p.hist + (size_t)s * D * M * p.Lsel + sc.sel_slot[l];
             int fs = fr0;
 #pragma unroll
             for (int f = 0; f < 2; f++) {
@@ -383,6 +465,7 @@ __global__ void __launch_bounds__(kSelThreads, ALGO == ALGO_LCMV ? 1 : 2) sel_pa
         sc.y[0][l] = y0; sc.y[1][l] = y1;
       }
     }
+    BF_PHASE(2);
     __syncthreads();   // (b)
     // ------------------------------------------------------------------ B1b: FP64 re-decision of guarded bins
     if (live && sc.n_recheck > 0) {
@@ -410,6 +493,10 @@ __global__ void __launch_bounds__(kSelThreads, ALGO == ALGO_LCMV ? 1 : 2) sel_pa
         }
     }
     __syncthreads();   // (c) work list complete
+    BF_PHASE(3);
+#ifdef BF_PHASE_TIMERS
+    ph_items += sc.n_items;
+#endif
     // ------------------------------------------------------------------ inverse of the PREVIOUS pair (last warp)
     if (warp == kSelWarps - 1 && ip > 0) {
       const int tp = t - 2;
@@ -455,46 +542,38 @@ __global__ void __launch_bounds__(kSelThreads, ALGO == ALGO_LCMV ? 1 : 2) sel_pa
     }
     if (live && ALGO != ALGO_GSS) {
       // mvdr / lcmv.  The spectrum tiles are dead after B1 (the current frame is in the ring too), so they become the
-      // staging area of the work list: every item thread pulls its P history frames + its own frame out of the ring
-      // with cp.async (8-byte pieces, coalesced across neighbouring items) in ONE round trip instead of walking P
-      // dependent loads, then builds the covariance from shared memory.  Items beyond the staging capacity take
-      // further batches.
-      const int per_item = (p.P + 1) * M;
-      const int stride = per_item | 1;                      // odd pitch in float2: conflict-free 8-byte accesses
-      int nb = (kSelWarps * 1024) / stride;
-      if (nb > kSelThreads) nb = kSelThreads;
-      float2* stg = ztiles;
+      // per-thread staging slots of the ring pipeline (RingPipe): one item per thread, all threads at once.
       const int n_items = sc.n_items;
-      for (int base = 0; base < n_items; base += nb) {
-        if (base > 0) __syncthreads();                      // previous batch consumed
+      for (int base = 0; base < n_items; base += kSelThreads) {
+        const int nb = min(n_items - base, kSelThreads);
+        const int cap = (kSelWarps * 1024) / nb;             // float2 of staging per item of this batch
         const int q = base + tid;
-        const bool on = tid < nb && q < n_items;
-        float2* hs = stg + (size_t)tid * stride;
-        int l = 0, f = 0;
-        if (on) {
-          l = sc.items[q] >> 1; f = sc.items[q] & 1;
-          const float2* ring_l = p.hist + (size_t)s * D * M * p.Lsel + p.sel_slot[l];
-          int slot = (fr0 + f - p.P) % D;                   // ring slot of frame (t+f) - P
-          if (slot < 0) slot += D;
-          for (int k = 0; k <= p.P; k++) {
-            const float2* src = ring_l + (size_t)slot * M * p.Lsel;
-            if (++slot == D) slot = 0;
-            for (int i = 0; i < M; i++)
-              asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(hs + k * M + i)), "l"(src + (size_t)i * p.Lsel) : "memory");
+        auto run = [&](auto depth_c) {
+          constexpr int kDepth = decltype(depth_c)::value;
+          const int pitch = (kDepth * M) | 1;                // odd pitch in float2: conflict-free 8-byte accesses
+          if (q < n_items) {
+            const int l = sc.items[q] >> 1, f = sc.items[q] & 1;
+            RingPipe<kDepth> pipe;
+            pipe.ring_l = p.hist + (size_t)s * D * M * p.Lsel + sc.sel_slot[l];
+            pipe.my = ztiles + (size_t)tid * pitch;
+            pipe.mic_stride = (size_t)p.Lsel;
+            pipe.slot_stride = (size_t)M * p.Lsel;
+            pipe.M = M; pipe.D = D; pipe.P = p.P;
+            int slot = (fr0 + f - p.P) % D;                  // ring slot of frame (t+f) - P
+            if (slot < 0) slot += D;
+            pipe.next_k = 0; pipe.next_ring = slot; pipe.next_stage = 0; pipe.read_stage = 0;
+            const float2* steer_l = p.steer + (size_t)l * p.C * M;
+            sc.y[f][l] = (ALGO == ALGO_MVDR) ? mvdr_ring_item<8, float>(p, pipe, steer_l) : lcmv_ring_item<8, double>(p, pipe, steer_l);
           }
-        }
-        asm volatile("cp.async.commit_group;" ::: "memory");
-        asm volatile("cp.async.wait_group 0;" ::: "memory");
-        if (on) {
-          float2 x[8];
-#pragma unroll
-          for (int ch = 0; ch < 8; ch++) x[ch] = (ch < M) ? hs[p.P * M + ch] : make_float2(0.f, 0.f);
-          const float2* steer_l = p.steer + (size_t)l * p.C * M;
-          sc.y[f][l] = (ALGO == ALGO_MVDR) ? mvdr_ring_item<8, float>(p, hs, x, steer_l) : lcmv_ring_item<8, double>(p, hs, x, steer_l);
-        }
+        };
+        if (cap > 11 * M) run(IC<11>{});                     // P + 1 <= 11 frames at once is the common launch value (P = 10)
+        else if (cap > 6 * M) run(IC<6>{});
+        else run(IC<3>{});
       }
     }
+    BF_PHASE(4);
     __syncthreads();   // (e) Y complete; G consumed by the inverse; Z no longer needed
+    BF_PHASE(5);
     if (use_tma && ip + 1 < npairs) {   // the spectrum tiles are free: stage the next pair's hops into them
       fence_proxy_async();
       issue(t + 2);
@@ -540,6 +619,14 @@ __global__ void __launch_bounds__(kSelThreads, ALGO == ALGO_LCMV ? 1 : 2) sel_pa
       }
     }
   }
+  BF_PHASE(6);
+#ifdef BF_PHASE_TIMERS
+  if (p.debug == 1 && blockIdx.x == 0 && (tid == 0 || tid == 255))
+    printf("sel_pairs phases (clk/pair, thread %d): A %lld | wait(a) %lld | B1 %lld | B1b+list %lld | own B2 %lld | wait(e) %lld | B3 %lld | items/pair %.1f\n",
+           tid, ph_clk[0] / npairs, ph_clk[1] / npairs, ph_clk[2] / npairs, ph_clk[3] / npairs, ph_clk[4] / npairs, ph_clk[5] / npairs,
+           ph_clk[6] / npairs, (double)ph_items / npairs);
+#endif
+#undef BF_PHASE
   __syncthreads();
   for (int i = tid; i < H; i += kSelThreads) p.tail[(size_t)s * H + i] = sc.tail[i];
 }
