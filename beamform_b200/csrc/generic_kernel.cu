@@ -28,7 +28,7 @@
 
 namespace bf {
 
-constexpr int kGenThreads = 256;
+constexpr int kGenThreads = 256;   // 8 warps x 255 registers: the radix-16 FP64 butterflies do not fit 128 registers (512 threads spilled 0.9 KB/thread)
 
 // XOR swizzle of a transform's element index (elements are 8 or 16 bytes): the first Stockham pass scatters with a
 // stride of R elements, which without it lands every lane of a warp in the same shared-memory bank group.
@@ -57,8 +57,8 @@ template <> struct VecOps<double2> {
 
 // One Stockham pass of radix R over `nfft` transforms of size NN stored back to back in z (in place).
 //   j in [0, NN/R): k = j mod Ns; v[q] = z[j + q*NN/R] * W_{Ns*R}^{k q}; V = DFT_R(v); z[(j/Ns)*Ns*R + k + q*Ns] = V[q]
-template <int NN, int R, int DIR, typename V>
-__device__ __forceinline__ void stockham_pass(V* z, int nfft, int Ns, const V* __restrict__ tw, int tid) {
+template <int NN, int R, int Ns, int DIR, typename V>
+__device__ __forceinline__ void stockham_pass(V* z, int nfft, const V* __restrict__ tw, int tid) {
   constexpr int per = NN / R;                                  // tasks per transform
   constexpr int g = kGenThreads / per > 0 ? kGenThreads / per : 1;   // transforms per round
   static_assert(per <= kGenThreads, "one round must cover a whole transform");
@@ -75,7 +75,7 @@ __device__ __forceinline__ void stockham_pass(V* z, int nfft, int Ns, const V* _
 #pragma unroll
       for (int q = 0; q < R; q++) {
         V a = zz[swz(j + q * per)];
-        if (q > 0) {
+        if (Ns > 1 && q > 0) {   // first pass: k = 0, every twiddle is 1
           const V w = __ldg(tw + ((tstep * q) & (NN - 1)));
           a = (DIR < 0) ? VecOps<V>::mul(a, w) : VecOps<V>::mulc(a, w);
         }
@@ -95,22 +95,22 @@ __device__ __forceinline__ void stockham_pass(V* z, int nfft, int Ns, const V* _
 template <int NN, int DIR, typename V>
 __device__ __forceinline__ void block_fft(V* z, int nfft, const V* __restrict__ tw, int tid) {
   if constexpr (NN == 4096) {
-    stockham_pass<NN, 16, DIR, V>(z, nfft, 1, tw, tid);
-    stockham_pass<NN, 16, DIR, V>(z, nfft, 16, tw, tid);
-    stockham_pass<NN, 16, DIR, V>(z, nfft, 256, tw, tid);
+    stockham_pass<NN, 16, 1, DIR, V>(z, nfft, tw, tid);
+    stockham_pass<NN, 16, 16, DIR, V>(z, nfft, tw, tid);
+    stockham_pass<NN, 16, 256, DIR, V>(z, nfft, tw, tid);
   } else if constexpr (NN == 2048) {
-    stockham_pass<NN, 16, DIR, V>(z, nfft, 1, tw, tid);
-    stockham_pass<NN, 16, DIR, V>(z, nfft, 16, tw, tid);
-    stockham_pass<NN, 8, DIR, V>(z, nfft, 256, tw, tid);
+    stockham_pass<NN, 16, 1, DIR, V>(z, nfft, tw, tid);
+    stockham_pass<NN, 16, 16, DIR, V>(z, nfft, tw, tid);
+    stockham_pass<NN, 8, 256, DIR, V>(z, nfft, tw, tid);
   } else if constexpr (NN == 1024) {
-    stockham_pass<NN, 16, DIR, V>(z, nfft, 1, tw, tid);
-    stockham_pass<NN, 8, DIR, V>(z, nfft, 16, tw, tid);
-    stockham_pass<NN, 8, DIR, V>(z, nfft, 128, tw, tid);
+    stockham_pass<NN, 16, 1, DIR, V>(z, nfft, tw, tid);
+    stockham_pass<NN, 8, 16, DIR, V>(z, nfft, tw, tid);
+    stockham_pass<NN, 8, 128, DIR, V>(z, nfft, tw, tid);
   } else {
     static_assert(NN == 512, "supported frame sizes: 512, 1024, 2048, 4096");
-    stockham_pass<NN, 8, DIR, V>(z, nfft, 1, tw, tid);
-    stockham_pass<NN, 8, DIR, V>(z, nfft, 8, tw, tid);
-    stockham_pass<NN, 8, DIR, V>(z, nfft, 64, tw, tid);
+    stockham_pass<NN, 8, 1, DIR, V>(z, nfft, tw, tid);
+    stockham_pass<NN, 8, 8, DIR, V>(z, nfft, tw, tid);
+    stockham_pass<NN, 8, 64, DIR, V>(z, nfft, tw, tid);
   }
 }
 
@@ -278,6 +278,199 @@ __device__ __forceinline__ void phase_pair_n(const KernelParams& p, int s, int t
   __syncthreads();
 }
 
+// Fused per-bin stage for small arrays (2 <= M <= 4, spectra of a bin held in registers): one pass over the bins
+// loads each microphone's packed double spectrum once, takes the mask decisions of BOTH frames, runs the MCRA /
+// post-filter recursion over the two frames with one state load and one store, and writes the Hermitian-assembled
+// G = Yh_t + i Yh_{t+1} straight into the inverse transform's buffer (phase.cpp:70-134, phasempf.cpp:193-302).
+// Two microphones (C4): |phi_0 - phi_1| wrapped equals |arg(z_0 conj z_1)|, z_i = conj(w_i) X_i, so the test
+// "< min_phase" is the sign of sin(thr)*Re(u) - cos(thr)*|Im(u)| (0 < thr < pi) and needs no arctangent; results within
+// FP32 rounding of the threshold are re-decided in double from the same double spectra (phase_decide_d).
+template <int ALGO, int NN, int MM>
+__device__ __forceinline__ void phase_pair_fused(const KernelParams& p, int s, int t, bool two, const double2* zall, float2* gbuf,
+                                                 int& cur_L, int& first_L, int tid, float sin_thr, float cos_thr) {
+  constexpr int H = NN / 2, L = NN / 2 + 2;
+  constexpr bool kGate = (ALGO == ALGO_PHASE);
+  constexpr bool kMpf = (ALGO == ALGO_PHASEMPF);
+  const int M = p.M, nf = two ? 2 : 1;
+  const int npairs = M * (M - 1) / 2;
+  const bool fast2 = (MM == 2) && p.min_phase_rad > 0.f && p.min_phase_rad < 3.1415925f;
+  // MCRA window bookkeeping (phasempf.cpp:162-176) is global per frame: resolve both frames up front
+  bool reset_f[2] = {false, false};
+  float inv_cl_f[2] = {1.f, 1.f};
+  int fst_f[2] = {first_L, first_L};
+  {
+    int cl = cur_L, fst = first_L;
+    if (kMpf) {
+      for (int f = 0; f < nf; f++) {
+        const bool r = cl > p.mcra_L;
+        if (r) { cl = 1; fst = 0; } else { cl++; }
+        reset_f[f] = r; inv_cl_f[f] = 1.0f / (float)cl; fst_f[f] = fst;
+      }
+    }
+    cur_L = cl;
+    first_L = fst;
+  }
+  float* stg = kMpf ? p.mpf_state + (size_t)s * 7 * L : nullptr;
+
+  auto eval_bin = [&](int l, float2& y0, float2& y1) {
+    const int j = (l == L - 1) ? H - 1 : l;   // pseudo-bin: conj of bin N/2-1 (SURVEY B-4)
+    float2 x[2][MM];
+#pragma unroll
+    for (int i = 0; i < MM; i++) {
+      if (i < M) {
+        const double2 a = zall[(size_t)i * NN + swz(j)], b = zall[(size_t)i * NN + swz((NN - j) & (NN - 1))];
+        x[0][i] = make_float2((float)(a.x + b.x), (float)(a.y - b.y));   // Z[j] + conj(Z[N-j])
+        x[1][i] = make_float2((float)(a.y + b.y), (float)(b.x - a.x));   // -i (Z[j] - conj(Z[N-j]))
+        if (l == L - 1) { x[0][i].y = -x[0][i].y; x[1][i].y = -x[1][i].y; }
+      } else {
+        x[0][i] = x[1][i] = make_float2(0.f, 0.f);
+      }
+    }
+    float2 wst[MM];
+    {
+      const float2* st = p.steer + (size_t)l * p.C * M;
+#pragma unroll
+      for (int i = 0; i < MM; i++) wst[i] = (i < M) ? st[i] : make_float2(1.f, 0.f);
+    }
+    float S_prev = 0.f, S_tmp = 0.f, S_min = 0.f, lam = 0.f, Zs = 0.f, rev0 = 0.f, rev1 = 0.f;
+    if (kMpf) {
+      S_prev = stg[0 * L + l]; S_tmp = stg[1 * L + l]; S_min = stg[2 * L + l]; lam = stg[3 * L + l];
+      Zs = stg[4 * L + l]; rev0 = stg[5 * L + l]; rev1 = stg[6 * L + l];
+    }
+    float2 yy[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+#pragma unroll
+    for (int f = 0; f < 2; f++) {
+      if (f >= nf) break;
+      float magsum = 0.f;
+      float2 zr[MM];
+#pragma unroll
+      for (int i = 0; i < MM; i++) {
+        const float2 xi = x[f][i];
+        if (i < M) magsum += sqrtf(fmaf(xi.x, xi.x, xi.y * xi.y));
+        zr[i] = make_float2(xi.x * wst[i].x + xi.y * wst[i].y, xi.y * wst[i].x - xi.x * wst[i].y);   // conj(w) x
+      }
+      unsigned fl = 0;
+      bool doubt = false;
+      if (fast2) {
+        const float d = zr[0].x * zr[1].x + zr[0].y * zr[1].y;    // Re(z0 conj z1)
+        const float c = zr[0].y * zr[1].x - zr[0].x * zr[1].y;    // Im(z0 conj z1)
+        const float a = sin_thr * d, b = cos_thr * fabsf(c);
+        const float q = a - b;                                      // |z0||z1| sin(thr - |dphi|)
+        if (q > 0.f) fl |= 2;
+        doubt = fabsf(q) <= 4.0e-6f * (fabsf(a) + fabsf(b));
+      } else {
+        float phi[MM];
+#pragma unroll
+        for (int i = 0; i < MM; i++) phi[i] = atan2f(zr[i].y, zr[i].x);
+        float tot = 0.f;
+#pragma unroll
+        for (int a = MM - 2; a >= 0; a--) {
+          float lvl = 0.f;
+#pragma unroll
+          for (int b = a + 1; b < MM; b++)
+            if (b < M) lvl += wrap_diff_n(phi[a], phi[b]);
+          if (a <= M - 2) tot = lvl + tot;
+        }
+        const float mean_diff = tot / (float)npairs;
+        if (mean_diff < p.min_phase_rad) fl |= 2;
+        doubt = fabsf(mean_diff - p.min_phase_rad) <= 4.0e-6f;
+      }
+      if (kGate) {
+        const float thr = p.thr_phase_mag;
+        if (magsum > thr) fl |= 1;
+        if (fabsf(magsum - thr) <= 2.0e-6f * thr) doubt = true;
+      } else {
+        fl |= 1;
+      }
+      if (doubt) fl = phase_decide_d<NN>(p, zall, l, f, kGate);
+      if (p.capture) {
+        unsigned char* cap = p.capture + (size_t)s * p.capture_stream_stride + (size_t)(t + f) * NN;
+        const unsigned char cf = (unsigned char)(((fl & 1) && (fl & 2)) ? 2 : 0);
+        if (l <= H) {
+          cap[l] = cf;
+          if (l > 0 && l < H - 1) cap[NN - l] = cf;
+        } else {
+          cap[H + 1] = cf;
+        }
+      }
+      // ---- output of this frame (same arithmetic as phase_pair_n) ----
+      const float2 x0 = x[f][0];
+      const float mag_mean = magsum / (float)M;
+      const float n0 = fmaf(x0.x, x0.x, x0.y * x0.y);
+      const float r0 = rsqrtf(n0);
+      const float2 unit = n0 > 0.f ? make_float2(x0.x * r0, x0.y * r0) : make_float2(1.f, 0.f);   // e^{i arg X_0}
+      float2 y;
+      if (ALGO == ALGO_PHASE) {
+        const float mag = ((fl & 1) && (fl & 2)) ? mag_mean : mag_mean * p.mag_mult;   // phase.cpp:114-123
+        y = make_float2(mag * unit.x, mag * unit.y);
+      } else {
+        const bool kept = (fl & 2) != 0;
+        const float soi = kept ? mag_mean : mag_mean * p.min_mag;   // phasempf.cpp:234-244
+        const float itf = kept ? mag_mean * p.min_mag : mag_mean;
+        const float s2 = soi * soi, i2 = itf * itf;
+        const float Sf = (l == 1) ? 0.75f * s2 : s2;   // SURVEY B-9: only bins 1 and N-1 are scaled
+        const float S = p.mcra_alphaS * S_prev + (1.0f - p.mcra_alphaS) * Sf;
+        if (reset_f[f]) { S_min = fminf(S_tmp, S); S_tmp = S; }
+        else { S_min = fminf(S_min, S); S_tmp = fminf(S_tmp, S); }
+        if (fst_f[f] || S < S_min * p.mcra_delta || lam > s2) {
+          if (fst_f[f] && inv_cl_f[f] > p.mcra_alphaD) lam = inv_cl_f[f] * lam + (1.0f - inv_cl_f[f]) * s2;
+          else lam = p.mcra_alphaD2 * lam + (1.0f - p.mcra_alphaD) * s2;   // SURVEY B-16
+        }
+        S_prev = S;
+        Zs = p.mpf_alphaS * Zs + (1.0f - p.mpf_alphaS) * i2;   // phasempf.cpp:255-271
+        rev0 = p.mpf_gamma * rev0 + p.mpf_rev_gain * s2;
+        rev1 = p.mpf_gamma * rev1 + p.mpf_rev_gain * i2;
+        const float Lam = sqrtf(lam + p.mpf_eta * Zs + rev0 + rev1);
+        float mag;
+        if (p.out_only_noise) {
+          mag = Lam * p.out_amp;
+        } else {
+          mag = p.out_only_mcra ? (soi - sqrtf(lam)) * p.out_amp : (soi - Lam) * p.out_amp;
+          if (mag < 0.f) mag = p.noise_floor;
+        }
+        const float2 u2 = soi > 0.f ? unit : make_float2(1.f, 0.f);
+        y = make_float2(mag * u2.x, mag * u2.y);
+      }
+      yy[f] = y;
+    }
+    if (kMpf) {
+      stg[0 * L + l] = S_prev; stg[1 * L + l] = S_tmp; stg[2 * L + l] = S_min; stg[3 * L + l] = lam;
+      stg[4 * L + l] = Zs; stg[5 * L + l] = rev0; stg[6 * L + l] = rev1;
+    }
+    y0 = yy[0];
+    y1 = yy[1];
+  };
+
+  // thread tid takes bins tid, tid + T, ...; bin 0 has no decision (phase.cpp:87, SURVEY B-5), so its thread takes the
+  // Nyquist bin instead, and the thread of bin N/2-1 also evaluates the pseudo-bin N/2+1 that is folded into it
+  for (int l0 = tid; l0 < H; l0 += kGenThreads) {
+    int l = l0;
+    if (l0 == 0) {
+      float2 g0 = make_float2(0.f, 0.f);
+      if (ALGO == ALGO_PHASE) {   // Y[0] = X_0[0] (real for real input); phasempf leaves bin 0 at 0
+        const double2 a = zall[swz(0)];
+        g0 = make_float2((float)(2.0 * a.x), two ? (float)(2.0 * a.y) : 0.f);
+      }
+      gbuf[swz(0)] = g0;
+      if (p.capture)
+        for (int f = 0; f < nf; f++) p.capture[(size_t)s * p.capture_stream_stride + (size_t)(t + f) * NN] = 0;
+      l = H;
+    }
+    float2 y0, y1;
+    eval_bin(l, y0, y1);
+    if (l == H - 1) {   // Hermitian part of the asymmetric pair (N/2-1, N/2+1): Yh = (Y[N/2-1] + conj(Y[N/2+1])) / 2
+      float2 p0, p1;
+      eval_bin(L - 1, p0, p1);
+      y0 = make_float2(0.5f * (y0.x + p0.x), 0.5f * (y0.y - p0.y));
+      y1 = make_float2(0.5f * (y1.x + p1.x), 0.5f * (y1.y - p1.y));
+    }
+    if (l == H) { y0.y = 0.f; y1.y = 0.f; }   // Re(): self-conjugate bin
+    gbuf[swz(l)] = make_float2(y0.x - y1.y, y0.y + y1.x);                          // Yh_t + i Yh_{t+1}
+    if (l < H) gbuf[swz(NN - l)] = make_float2(y0.x + y1.y, y1.x - y0.y);          // conj(Yh_t) + i conj(Yh_{t+1})
+  }
+}
+
+
 template <int ALGO, int NN>
 __global__ void __launch_bounds__(kGenThreads, 1) frames_kernel_n(const KernelParams p) {
   constexpr int H = NN / 2, L = NN / 2 + 2;
@@ -294,6 +487,12 @@ __global__ void __launch_bounds__(kGenThreads, 1) frames_kernel_n(const KernelPa
   const float2* tw = p.twid_f;
   const float* win = p.win_f;
   int cur_L = p.mcra_cur_L0, first_L = p.mcra_first0;
+  float sin_thr = 0.f, cos_thr = 1.f;
+  if (kPha) {
+    double sd, cd;
+    sincos(p.min_phase_rad_d, &sd, &cd);
+    sin_thr = (float)sd; cos_thr = (float)cd;
+  }
 
   for (int i = tid; i < H; i += kGenThreads) sc.tail[i] = p.tail[(size_t)s * H + i];
   if (kSmooth)
@@ -312,18 +511,20 @@ __global__ void __launch_bounds__(kGenThreads, 1) frames_kernel_n(const KernelPa
       const float* hb = base + (size_t)t * H;
       const float* hc = two ? base + (size_t)(t + 1) * H : hb;
       // first half of the frames: (hop t-1, hop t); second half: (hop t, hop t+1); loads of a half are issued together
-      constexpr int kIter = H / kGenThreads;
+      constexpr int kIter = (H + kGenThreads - 1) / kGenThreads;
       float fa[kIter], fb[kIter], fc[kIter];
 #pragma unroll
       for (int k = 0; k < kIter; k++) {
         const int n = tid + k * kGenThreads;
-        fa[k] = __ldg(ha + n);
-        fb[k] = __ldg(hb + n);
-        fc[k] = two ? __ldg(hc + n) : 0.f;
+        const bool in = (H % kGenThreads == 0) || n < H;
+        fa[k] = in ? __ldg(ha + n) : 0.f;
+        fb[k] = in ? __ldg(hb + n) : 0.f;
+        fc[k] = (in && two) ? __ldg(hc + n) : 0.f;
       }
 #pragma unroll
       for (int k = 0; k < kIter; k++) {
         const int n = tid + k * kGenThreads;
+        if ((H % kGenThreads != 0) && n >= H) continue;
         const float b1 = two ? fb[k] : 0.f;
         if constexpr (kPha) {
           const double w0 = 0.5 * p.win_d[n], w1 = 0.5 * p.win_d[n + H];
@@ -353,7 +554,12 @@ __global__ void __launch_bounds__(kGenThreads, 1) frames_kernel_n(const KernelPa
         gbuf[swz(j)] = make_float2(2.0f * acc.x, 2.0f * acc.y);
       }
     } else {
-      phase_pair_n<ALGO, NN>(p, s, t, two, zall, sc, cur_L, first_L, tid);
+      if (M >= 2 && M <= 4) {
+        if (M == 2) phase_pair_fused<ALGO, NN, 2>(p, s, t, two, zall, gbuf, cur_L, first_L, tid, sin_thr, cos_thr);
+        else if (M == 3) phase_pair_fused<ALGO, NN, 3>(p, s, t, two, zall, gbuf, cur_L, first_L, tid, sin_thr, cos_thr);
+        else phase_pair_fused<ALGO, NN, 4>(p, s, t, two, zall, gbuf, cur_L, first_L, tid, sin_thr, cos_thr);
+      } else {
+            phase_pair_n<ALGO, NN>(p, s, t, two, zall, sc, cur_L, first_L, tid);
       for (int l = tid; l <= H; l += kGenThreads) {   // Hermitian assembly of G = Yh_t + i Yh_{t+1}
         float2 y0 = sc.y[0][l], y1 = two ? sc.y[1][l] : make_float2(0.f, 0.f);
         if (l == H - 1) {
@@ -378,6 +584,7 @@ __global__ void __launch_bounds__(kGenThreads, 1) frames_kernel_n(const KernelPa
               cap[H + 1] = fl;
             }
           }
+      }
       }
     }
     __syncthreads();
