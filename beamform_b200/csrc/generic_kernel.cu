@@ -20,11 +20,27 @@
 // The 1024-point frames of the headline configurations use the register-resident warp FFT kernels
 // (das_kernel.cu, sel_kernel.cu, frames_kernel.cu); this kernel covers the other frame sizes, notably the
 // 4096-point PhaseMPF configuration C4.
+#include <cstdio>
 #include <type_traits>
 
 #include "bf_device.h"
 #include "fft_reg.cuh"
 #include "fft_reg_d.cuh"
+#include "warp_fft1024.cuh"
+
+// tuning switches (profiling builds override them with -D)
+#ifndef BF_GEN_FWD_PIPE
+#define BF_GEN_FWD_PIPE 0
+#endif
+#ifndef BF_GEN_INV_OOP
+#define BF_GEN_INV_OOP 1
+#endif
+#ifndef BF_GEN_PACK_PAIR
+#define BF_GEN_PACK_PAIR 0
+#endif
+#ifndef BF_GEN_PREFETCH
+#define BF_GEN_PREFETCH 1
+#endif
 
 namespace bf {
 
@@ -55,39 +71,80 @@ template <> struct VecOps<double2> {
   template <int R, int DIR> static __device__ __forceinline__ void fft(double2* v) { fft_dit_d<R, DIR>(v); }
 };
 
-// One Stockham pass of radix R over `nfft` transforms of size NN stored back to back in z (in place).
-//   j in [0, NN/R): k = j mod Ns; v[q] = z[j + q*NN/R] * W_{Ns*R}^{k q}; V = DFT_R(v); z[(j/Ns)*Ns*R + k + q*Ns] = V[q]
-template <int NN, int R, int Ns, int DIR, typename V>
-__device__ __forceinline__ void stockham_pass(V* z, int nfft, const V* __restrict__ tw, int tid) {
-  constexpr int per = NN / R;                                  // tasks per transform
+// ---- shared-memory Stockham FFT, code-size first ----
+// The kernel's hot loop has to live in the instruction caches (8 warps per SM execute it once per frame pair: with
+// every pass unrolled into its own copy the 4096-point PhaseMPF kernel was 1.2 MB of SASS and a third of all issue
+// slots waited for instruction fetch).  So the pass index is a RUN-TIME loop variable: one copy of the radix-R
+// gather/twiddle/butterfly body and one of the scatter per radix and element type.
+//   pass with Ns = 1 << sh:  j in [0, NN/R): k = j mod Ns; v[q] = z[j + q*NN/R] * W_{Ns*R}^{k q}; V = DFT_R(v);
+//                            z[(j - k)*R + k + q*Ns] = V[q]
+template <int NN, int R, int DIR, typename V>
+struct Step {
+  static constexpr int per = NN / R;   // tasks per transform
+  static __device__ __forceinline__ void load(const V* zz, const V* __restrict__ tw, int j, int sh, V (&v)[R]) {
+    const int k = j & ((1 << sh) - 1);
+    // Twiddles W^q, q = 1..R-1, W = W_NN^{k * per >> sh}: ONE table load, then products, instead of R-1 loads: with
+    // 225 KB of the SM given to shared memory the 64 KB double table does not stay in L1 and every load paid an L2 round
+    // trip.  FP32: product tree of depth <= 4 (W^2, W^4, W^8 by squaring, the rest as products of two of those) so the
+    // rounding stays at ~4 ulp.  FP64: running product W^q = W^(q-1) * W (two live values; 15 roundings of 1e-16).
+    constexpr bool kDouble = sizeof(V) == sizeof(double2);
+    V w[kDouble ? 2 : R];
+    if (sh > 0) {   // the first pass has k = 0: unit twiddles
+      w[1] = __ldg(tw + k * (per >> sh));
+      if constexpr (!kDouble) {
+        static_for<2, R>([&](auto qc) {
+          constexpr int q = decltype(qc)::value;
+          constexpr int hi = 1 << ilog2(q), lo = q - hi;       // q = hi + lo, hi the top bit
+          if constexpr (lo == 0) w[q] = VecOps<V>::mul(w[q / 2], w[q / 2]);
+          else w[q] = VecOps<V>::mul(w[hi], w[lo]);
+        });
+      } else {
+        w[0] = w[1];
+      }
+    }
+    static_for<0, R>([&](auto qc) {
+      constexpr int q = decltype(qc)::value;
+      V a = zz[swz(j + q * per)];
+      if (q > 0 && sh > 0) {
+        if constexpr (kDouble) {
+          a = (DIR < 0) ? VecOps<V>::mul(a, w[0]) : VecOps<V>::mulc(a, w[0]);
+          if (q + 1 < R) w[0] = VecOps<V>::mul(w[0], w[1]);
+        } else {
+          a = (DIR < 0) ? VecOps<V>::mul(a, w[q]) : VecOps<V>::mulc(a, w[q]);
+        }
+      }
+      v[brev(q, ilog2(R))] = a;
+    });
+    VecOps<V>::template fft<R, DIR>(v);
+  }
+  static __device__ __forceinline__ void store(V* zz, int j, int sh, const V (&v)[R]) {
+    const int k = j & ((1 << sh) - 1);
+    const int j0 = (j - k) * R + k;
+#pragma unroll
+    for (int q = 0; q < R; q++) zz[swz(j0 + (q << sh))] = v[q];
+  }
+};
+
+// n_pass in-place passes of radix R, Ns = 1 << sh0, then * R per pass, over nfft transforms stored back to back.
+// Every read of a round precedes every write: two block barriers per round.
+template <int NN, int R, int DIR, typename V>
+__device__ __forceinline__ void passes_inplace(V* z, int nfft, const V* __restrict__ tw, int tid, int sh0, int n_pass) {
+  typedef Step<NN, R, DIR, V> S;
+  constexpr int per = S::per;
   constexpr int g = kGenThreads / per > 0 ? kGenThreads / per : 1;   // transforms per round
   static_assert(per <= kGenThreads, "one round must cover a whole transform");
   const int f_local = tid / per, j = tid - f_local * per;
-  const int k = j & (Ns - 1);
-  const int tstep = k * (NN / (Ns * R));                      // twiddle index step: W_NN^{tstep*q}
-  const int j0 = (j / Ns) * Ns * R + k;
-  for (int f0 = 0; f0 < nfft; f0 += g) {
-    const int f = f0 + f_local;
+  const int rounds = (nfft + g - 1) / g;
+#pragma unroll 1
+  for (int it = 0; it < n_pass * rounds; it++) {
+    const int pass = it / rounds, f = (it - pass * rounds) * g + f_local;
+    const int sh = sh0 + pass * ilog2(R);
     const bool on = f_local < g && f < nfft;
     V v[R];
     V* zz = z + (size_t)f * NN;
-    if (on) {
-#pragma unroll
-      for (int q = 0; q < R; q++) {
-        V a = zz[swz(j + q * per)];
-        if (Ns > 1 && q > 0) {   // first pass: k = 0, every twiddle is 1
-          const V w = __ldg(tw + ((tstep * q) & (NN - 1)));
-          a = (DIR < 0) ? VecOps<V>::mul(a, w) : VecOps<V>::mulc(a, w);
-        }
-        v[brev(q, ilog2(R))] = a;
-      }
-      VecOps<V>::template fft<R, DIR>(v);
-    }
-    __syncthreads();   // every read of this round precedes every write
-    if (on) {
-#pragma unroll
-      for (int q = 0; q < R; q++) zz[swz(j0 + q * Ns)] = v[q];
-    }
+    if (on) S::load(zz, tw, j, sh, v);
+    __syncthreads();
+    if (on) S::store(zz, j, sh, v);
     __syncthreads();
   }
 }
@@ -95,23 +152,76 @@ __device__ __forceinline__ void stockham_pass(V* z, int nfft, const V* __restric
 template <int NN, int DIR, typename V>
 __device__ __forceinline__ void block_fft(V* z, int nfft, const V* __restrict__ tw, int tid) {
   if constexpr (NN == 4096) {
-    stockham_pass<NN, 16, 1, DIR, V>(z, nfft, tw, tid);
-    stockham_pass<NN, 16, 16, DIR, V>(z, nfft, tw, tid);
-    stockham_pass<NN, 16, 256, DIR, V>(z, nfft, tw, tid);
+    passes_inplace<NN, 16, DIR, V>(z, nfft, tw, tid, 0, 3);
   } else if constexpr (NN == 2048) {
-    stockham_pass<NN, 16, 1, DIR, V>(z, nfft, tw, tid);
-    stockham_pass<NN, 16, 16, DIR, V>(z, nfft, tw, tid);
-    stockham_pass<NN, 8, 256, DIR, V>(z, nfft, tw, tid);
+    passes_inplace<NN, 16, DIR, V>(z, nfft, tw, tid, 0, 2);
+    passes_inplace<NN, 8, DIR, V>(z, nfft, tw, tid, 8, 1);
   } else if constexpr (NN == 1024) {
-    stockham_pass<NN, 16, 1, DIR, V>(z, nfft, tw, tid);
-    stockham_pass<NN, 8, 16, DIR, V>(z, nfft, tw, tid);
-    stockham_pass<NN, 8, 128, DIR, V>(z, nfft, tw, tid);
+    passes_inplace<NN, 16, DIR, V>(z, nfft, tw, tid, 0, 1);
+    passes_inplace<NN, 8, DIR, V>(z, nfft, tw, tid, 4, 2);
   } else {
     static_assert(NN == 512, "supported frame sizes: 512, 1024, 2048, 4096");
-    stockham_pass<NN, 8, 1, DIR, V>(z, nfft, tw, tid);
-    stockham_pass<NN, 8, 8, DIR, V>(z, nfft, tw, tid);
-    stockham_pass<NN, 8, 64, DIR, V>(z, nfft, tw, tid);
+    passes_inplace<NN, 8, DIR, V>(z, nfft, tw, tid, 0, 3);
   }
+}
+
+// Out-of-place passes of ONE transform, ping-pong between two buffers: writes cannot clobber the pass's own reads,
+// so one barrier per pass.  Returns the buffer that holds the result.
+template <int NN, int R, int DIR, typename V>
+__device__ __forceinline__ V* passes_oop(V* src, V* dst, const V* __restrict__ tw, int tid, int sh0, int n_pass) {
+  typedef Step<NN, R, DIR, V> S;
+  static_assert(S::per <= kGenThreads, "one round must cover a whole transform");
+#pragma unroll 1
+  for (int pass = 0; pass < n_pass; pass++) {
+    if (tid < S::per) {
+      V v[R];
+      S::load(src, tw, tid, sh0 + pass * ilog2(R), v);
+      S::store(dst, tid, sh0 + pass * ilog2(R), v);
+    }
+    __syncthreads();
+    V* t = src; src = dst; dst = t;
+  }
+  return src;
+}
+template <int NN, int DIR, typename V>
+__device__ __forceinline__ V* block_fft_oop(V* a, V* b, const V* __restrict__ tw, int tid) {
+  if constexpr (NN == 4096) {
+    return passes_oop<NN, 16, DIR, V>(a, b, tw, tid, 0, 3);
+  } else if constexpr (NN == 2048) {
+    V* r = passes_oop<NN, 16, DIR, V>(a, b, tw, tid, 0, 2);
+    return passes_oop<NN, 8, DIR, V>(r, r == a ? b : a, tw, tid, 8, 1);
+  } else if constexpr (NN == 1024) {
+    V* r = passes_oop<NN, 16, DIR, V>(a, b, tw, tid, 0, 1);
+    return passes_oop<NN, 8, DIR, V>(r, r == a ? b : a, tw, tid, 4, 2);
+  } else {
+    return passes_oop<NN, 8, DIR, V>(a, b, tw, tid, 0, 3);
+  }
+}
+
+// In-place 4096-point transforms of nfft >= 2 arrays, software-pipelined across the arrays: the step order is
+// (pass 0: f = 0..nfft-1), (pass 1: ...), (pass 2: ...); a step's results are written AFTER the next barrier, together
+// with the next step's reads (which touch another array, or this array one full barrier after its last write), so every
+// step costs one barrier and its stores overlap the next step's loads.  One step = all 256 threads (4096 / 16 tasks).
+template <int DIR, typename V>
+__device__ __forceinline__ void block_fft4096_multi(V* z, int nfft, const V* __restrict__ tw, int tid) {
+  typedef Step<4096, 16, DIR, V> S;
+  static_assert(S::per == kGenThreads, "one step per transform");
+  V v[16];
+  const int steps = 3 * nfft;
+  int f = 0, sh = 0, pf = 0, psh = 0;   // current and previous (array, pass shift)
+#pragma unroll 1
+  for (int i = 0; i <= steps; i++) {
+    if (i > 0) {
+      __syncthreads();
+      S::store(z + (size_t)pf * 4096, tid, psh, v);
+    }
+    if (i < steps) {
+      S::load(z + (size_t)f * 4096, tw, tid, sh, v);
+      pf = f; psh = sh;
+      if (++f == nfft) { f = 0; sh += 4; }
+    }
+  }
+  __syncthreads();
 }
 
 // X_i[j] of frame f from the packed half-scaled double spectrum Z = FFT(0.5*w*(x_t + i x_{t+1}))
@@ -134,7 +244,7 @@ __device__ __forceinline__ float wrap_diff_n(float a, float b) {   // phase.cpp:
 
 // Decision of one (bin, frame) in double from the double spectra (phase.cpp:89-123, phasempf.cpp:212-248)
 template <int NN>
-__device__ __forceinline__ unsigned phase_decide_d(const KernelParams& p, const double2* zall, int l, int f, bool use_gate) {
+__device__ __noinline__ unsigned phase_decide_d(const KernelParams& p, const double2* zall, int l, int f, bool use_gate) {
   double phi[BF_MAX_MICS_DEV];
   double magsum = 0.0;
   for (int ch = 0; ch < p.M; ch++) {
@@ -312,40 +422,46 @@ __device__ __forceinline__ void phase_pair_fused(const KernelParams& p, int s, i
   }
   float* stg = kMpf ? p.mpf_state + (size_t)s * 7 * L : nullptr;
 
-  auto eval_bin = [&](int l, float2& y0, float2& y1) {
-    const int j = (l == L - 1) ? H - 1 : l;   // pseudo-bin: conj of bin N/2-1 (SURVEY B-4)
+  // A bin is evaluated in three straight-line stages so that the U bins a thread carries per trip interleave in the
+  // instruction stream (8 warps per SM: the latency of a bin's load -> decision -> recursion chain has to be hidden by
+  // the thread's own independent bins):  A loads + mask decisions,  B rare FP64 re-decision,  C recursion + output.
+  struct Bin {
     float2 x[2][MM];
+    float st[7];       // phasempf state of the bin: S_prev, S_tmp, S_min, lambda_noise, Z, rev0, rev1
+    float magsum[2];
+    unsigned fl[2];
+    bool doubt[2];
+  };
+  auto stage_a = [&](int l, Bin& B) {
+    const int j = (l == L - 1) ? H - 1 : l;   // pseudo-bin: conj of bin N/2-1 (SURVEY B-4)
+    if (kMpf) {
 #pragma unroll
-    for (int i = 0; i < MM; i++) {
-      if (i < M) {
-        const double2 a = zall[(size_t)i * NN + swz(j)], b = zall[(size_t)i * NN + swz((NN - j) & (NN - 1))];
-        x[0][i] = make_float2((float)(a.x + b.x), (float)(a.y - b.y));   // Z[j] + conj(Z[N-j])
-        x[1][i] = make_float2((float)(a.y + b.y), (float)(b.x - a.x));   // -i (Z[j] - conj(Z[N-j]))
-        if (l == L - 1) { x[0][i].y = -x[0][i].y; x[1][i].y = -x[1][i].y; }
-      } else {
-        x[0][i] = x[1][i] = make_float2(0.f, 0.f);
-      }
+      for (int k = 0; k < 7; k++) B.st[k] = stg[k * L + l];
     }
     float2 wst[MM];
     {
       const float2* st = p.steer + (size_t)l * p.C * M;
 #pragma unroll
-      for (int i = 0; i < MM; i++) wst[i] = (i < M) ? st[i] : make_float2(1.f, 0.f);
+      for (int i = 0; i < MM; i++) wst[i] = (i < M) ? __ldg(st + i) : make_float2(1.f, 0.f);
     }
-    float S_prev = 0.f, S_tmp = 0.f, S_min = 0.f, lam = 0.f, Zs = 0.f, rev0 = 0.f, rev1 = 0.f;
-    if (kMpf) {
-      S_prev = stg[0 * L + l]; S_tmp = stg[1 * L + l]; S_min = stg[2 * L + l]; lam = stg[3 * L + l];
-      Zs = stg[4 * L + l]; rev0 = stg[5 * L + l]; rev1 = stg[6 * L + l];
+#pragma unroll
+    for (int i = 0; i < MM; i++) {
+      if (i < M) {
+        const double2 a = zall[(size_t)i * NN + swz(j)], b = zall[(size_t)i * NN + swz((NN - j) & (NN - 1))];
+        B.x[0][i] = make_float2((float)(a.x + b.x), (float)(a.y - b.y));   // Z[j] + conj(Z[N-j])
+        B.x[1][i] = make_float2((float)(a.y + b.y), (float)(b.x - a.x));   // -i (Z[j] - conj(Z[N-j]))
+        if (l == L - 1) { B.x[0][i].y = -B.x[0][i].y; B.x[1][i].y = -B.x[1][i].y; }
+      } else {
+        B.x[0][i] = B.x[1][i] = make_float2(0.f, 0.f);
+      }
     }
-    float2 yy[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
 #pragma unroll
     for (int f = 0; f < 2; f++) {
-      if (f >= nf) break;
       float magsum = 0.f;
       float2 zr[MM];
 #pragma unroll
       for (int i = 0; i < MM; i++) {
-        const float2 xi = x[f][i];
+        const float2 xi = B.x[f][i];
         if (i < M) magsum += sqrtf(fmaf(xi.x, xi.x, xi.y * xi.y));
         zr[i] = make_float2(xi.x * wst[i].x + xi.y * wst[i].y, xi.y * wst[i].x - xi.x * wst[i].y);   // conj(w) x
       }
@@ -382,7 +498,22 @@ __device__ __forceinline__ void phase_pair_fused(const KernelParams& p, int s, i
       } else {
         fl |= 1;
       }
-      if (doubt) fl = phase_decide_d<NN>(p, zall, l, f, kGate);
+      B.magsum[f] = magsum; B.fl[f] = fl; B.doubt[f] = doubt && f < nf;
+    }
+  };
+  auto stage_b = [&](int l, Bin& B) {
+#pragma unroll
+    for (int f = 0; f < 2; f++)
+      if (B.doubt[f]) B.fl[f] = phase_decide_d<NN>(p, zall, l, f, kGate);
+  };
+  const float inv_M = 1.0f / (float)M;
+  auto stage_c = [&](int l, Bin& B, float2& y0, float2& y1) {
+    float2 yy[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+    float S_prev = B.st[0], S_tmp = B.st[1], S_min = B.st[2], lam = B.st[3], Zs = B.st[4], rev0 = B.st[5], rev1 = B.st[6];
+#pragma unroll
+    for (int f = 0; f < 2; f++) {
+      if (f >= nf) break;
+      const unsigned fl = B.fl[f];
       if (p.capture) {
         unsigned char* cap = p.capture + (size_t)s * p.capture_stream_stride + (size_t)(t + f) * NN;
         const unsigned char cf = (unsigned char)(((fl & 1) && (fl & 2)) ? 2 : 0);
@@ -393,9 +524,8 @@ __device__ __forceinline__ void phase_pair_fused(const KernelParams& p, int s, i
           cap[H + 1] = cf;
         }
       }
-      // ---- output of this frame (same arithmetic as phase_pair_n) ----
-      const float2 x0 = x[f][0];
-      const float mag_mean = magsum / (float)M;
+      const float2 x0 = B.x[f][0];
+      const float mag_mean = B.magsum[f] * inv_M;
       const float n0 = fmaf(x0.x, x0.x, x0.y * x0.y);
       const float r0 = rsqrtf(n0);
       const float2 unit = n0 > 0.f ? make_float2(x0.x * r0, x0.y * r0) : make_float2(1.f, 0.f);   // e^{i arg X_0}
@@ -410,12 +540,13 @@ __device__ __forceinline__ void phase_pair_fused(const KernelParams& p, int s, i
         const float s2 = soi * soi, i2 = itf * itf;
         const float Sf = (l == 1) ? 0.75f * s2 : s2;   // SURVEY B-9: only bins 1 and N-1 are scaled
         const float S = p.mcra_alphaS * S_prev + (1.0f - p.mcra_alphaS) * Sf;
-        if (reset_f[f]) { S_min = fminf(S_tmp, S); S_tmp = S; }
-        else { S_min = fminf(S_min, S); S_tmp = fminf(S_tmp, S); }
-        if (fst_f[f] || S < S_min * p.mcra_delta || lam > s2) {
-          if (fst_f[f] && inv_cl_f[f] > p.mcra_alphaD) lam = inv_cl_f[f] * lam + (1.0f - inv_cl_f[f]) * s2;
-          else lam = p.mcra_alphaD2 * lam + (1.0f - p.mcra_alphaD) * s2;   // SURVEY B-16
-        }
+        const float m_min = reset_f[f] ? S_tmp : S_min;
+        S_min = fminf(m_min, S);
+        S_tmp = reset_f[f] ? S : fminf(S_tmp, S);
+        const bool upd = fst_f[f] || S < S_min * p.mcra_delta || lam > s2;
+        const bool avg = fst_f[f] && inv_cl_f[f] > p.mcra_alphaD;
+        const float ca = avg ? inv_cl_f[f] : p.mcra_alphaD2, cb = avg ? 1.0f - inv_cl_f[f] : 1.0f - p.mcra_alphaD;   // SURVEY B-16
+        lam = upd ? ca * lam + cb * s2 : lam;
         S_prev = S;
         Zs = p.mpf_alphaS * Zs + (1.0f - p.mpf_alphaS) * i2;   // phasempf.cpp:255-271
         rev0 = p.mpf_gamma * rev0 + p.mpf_rev_gain * s2;
@@ -441,32 +572,65 @@ __device__ __forceinline__ void phase_pair_fused(const KernelParams& p, int s, i
     y1 = yy[1];
   };
 
-  // thread tid takes bins tid, tid + T, ...; bin 0 has no decision (phase.cpp:87, SURVEY B-5), so its thread takes the
-  // Nyquist bin instead, and the thread of bin N/2-1 also evaluates the pseudo-bin N/2+1 that is folded into it
-  for (int l0 = tid; l0 < H; l0 += kGenThreads) {
-    int l = l0;
-    if (l0 == 0) {
-      float2 g0 = make_float2(0.f, 0.f);
-      if (ALGO == ALGO_PHASE) {   // Y[0] = X_0[0] (real for real input); phasempf leaves bin 0 at 0
-        const double2 a = zall[swz(0)];
-        g0 = make_float2((float)(2.0 * a.x), two ? (float)(2.0 * a.y) : 0.f);
+  // Thread tid takes bins tid, tid + T, ..., U per trip.  Bin 0 has no decision (phase.cpp:87, SURVEY B-5), so its
+  // thread takes the Nyquist bin instead; the pseudo-bin N/2+1 is evaluated in one extra trip by the thread that owns
+  // bin N/2-1 (same code, no second copy in the instruction stream) and folded into what that thread wrote for N/2-1.
+  constexpr int U = 2;
+  constexpr int kTrips = (H + U * kGenThreads - 1) / (U * kGenThreads);
+  if (tid == 0) {
+    float2 g0 = make_float2(0.f, 0.f);
+    if (ALGO == ALGO_PHASE) {   // Y[0] = X_0[0] (real for real input); phasempf leaves bin 0 at 0
+      const double2 a = zall[swz(0)];
+      g0 = make_float2((float)(2.0 * a.x), two ? (float)(2.0 * a.y) : 0.f);
+    }
+    gbuf[swz(0)] = g0;
+    if (p.capture)
+      for (int f = 0; f < nf; f++) p.capture[(size_t)s * p.capture_stream_stride + (size_t)(t + f) * NN] = 0;
+  }
+#pragma unroll 1
+  for (int trip = 0; trip <= kTrips; trip++) {
+    int lu[U];
+    bool on[U];
+    Bin B[U];
+    float2 y0[U], y1[U];
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      lu[u] = tid + (trip * U + u) * kGenThreads;
+      on[u] = trip < kTrips && lu[u] < H;
+      if (!on[u]) lu[u] = 1;
+      if (lu[u] == 0) lu[u] = H;
+    }
+    if (trip == kTrips && tid == ((H - 1) % kGenThreads)) { on[0] = true; lu[0] = L - 1; }
+    bool any = false;
+#pragma unroll
+    for (int u = 0; u < U; u++) any |= on[u];
+    if (!any) continue;
+#pragma unroll
+    for (int u = 0; u < U; u++) stage_a(lu[u], B[u]);
+#pragma unroll
+    for (int u = 0; u < U; u++)
+      if (on[u]) stage_b(lu[u], B[u]);
+#pragma unroll
+    for (int u = 0; u < U; u++)
+      if (on[u]) stage_c(lu[u], B[u], y0[u], y1[u]);
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      if (!on[u]) continue;
+      int l = lu[u];
+      float2 a0 = y0[u], a1 = y1[u];
+      if (l == L - 1) {
+        // Hermitian part of the asymmetric pair (N/2-1, N/2+1): Yh = (Y[N/2-1] + conj(Y[N/2+1])) / 2; Y[N/2-1] of both
+        // frames is recovered from this thread's own earlier stores
+        l = H - 1;
+        const float2 g = gbuf[swz(l)], g2 = gbuf[swz(NN - l)];
+        const float2 b0 = make_float2(0.5f * (g.x + g2.x), 0.5f * (g.y - g2.y)), b1 = make_float2(0.5f * (g.y + g2.y), 0.5f * (g2.x - g.x));
+        a0 = make_float2(0.5f * (b0.x + a0.x), 0.5f * (b0.y - a0.y));
+        a1 = make_float2(0.5f * (b1.x + a1.x), 0.5f * (b1.y - a1.y));
       }
-      gbuf[swz(0)] = g0;
-      if (p.capture)
-        for (int f = 0; f < nf; f++) p.capture[(size_t)s * p.capture_stream_stride + (size_t)(t + f) * NN] = 0;
-      l = H;
+      if (l == H) { a0.y = 0.f; a1.y = 0.f; }   // Re(): self-conjugate bin
+      gbuf[swz(l)] = make_float2(a0.x - a1.y, a0.y + a1.x);                          // Yh_t + i Yh_{t+1}
+      if (l < H) gbuf[swz(NN - l)] = make_float2(a0.x + a1.y, a1.x - a0.y);          // conj(Yh_t) + i conj(Yh_{t+1})
     }
-    float2 y0, y1;
-    eval_bin(l, y0, y1);
-    if (l == H - 1) {   // Hermitian part of the asymmetric pair (N/2-1, N/2+1): Yh = (Y[N/2-1] + conj(Y[N/2+1])) / 2
-      float2 p0, p1;
-      eval_bin(L - 1, p0, p1);
-      y0 = make_float2(0.5f * (y0.x + p0.x), 0.5f * (y0.y - p0.y));
-      y1 = make_float2(0.5f * (y1.x + p1.x), 0.5f * (y1.y - p1.y));
-    }
-    if (l == H) { y0.y = 0.f; y1.y = 0.f; }   // Re(): self-conjugate bin
-    gbuf[swz(l)] = make_float2(y0.x - y1.y, y0.y + y1.x);                          // Yh_t + i Yh_{t+1}
-    if (l < H) gbuf[swz(NN - l)] = make_float2(y0.x + y1.y, y1.x - y0.y);          // conj(Yh_t) + i conj(Yh_{t+1})
   }
 }
 
@@ -487,6 +651,11 @@ __global__ void __launch_bounds__(kGenThreads, 1) frames_kernel_n(const KernelPa
   const float2* tw = p.twid_f;
   const float* win = p.win_f;
   int cur_L = p.mcra_cur_L0, first_L = p.mcra_first0;
+  double win_s = 0.0, win_c = 0.0;   // 0.5 * (sin, cos)(pi * tid / N)
+  if (kPha) {
+    sincospi((double)tid / (double)NN, &win_s, &win_c);
+    win_s *= 0.5; win_c *= 0.5;
+  }
   float sin_thr = 0.f, cos_thr = 1.f;
   if (kPha) {
     double sd, cd;
@@ -501,18 +670,32 @@ __global__ void __launch_bounds__(kGenThreads, 1) frames_kernel_n(const KernelPa
 
   const int nh = p.hop_end - p.hop_begin;
   const int npairs = (nh + 1) >> 1;
+#ifdef BF_PHASE_TIMERS   // nvcc -DBF_PHASE_TIMERS + env BF_DEBUG=1: per-phase cycle totals of CTA 0 (profiling builds only)
+  long long ph_clk[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  long long ph_t = clock64();
+#define BF_PHASE(i) do { if (p.debug == 1) { __syncthreads(); const long long n_ = clock64(); ph_clk[i] += n_ - ph_t; ph_t = n_; } } while (0)
+#else
+#define BF_PHASE(i) do { } while (0)
+#endif
   for (int ip = 0; ip < npairs; ip++) {
     const int t = p.hop_begin + 2 * ip;
     const bool two = t + 1 < p.hop_end;
     // ---- window + pack: z = 0.5*w*(frame_t + i*frame_{t+1}), frame_t = [hop t-1 | hop t] (util.h:217-242) ----
-    for (int ch = 0; ch < M; ch++) {
+    // the next pair's two new hops start their trip from HBM to L2 now, one 128-byte line per request
+    if (BF_GEN_PREFETCH && t + 2 < p.hop_end) {
+      const int lines_per_mic = ((t + 3 < p.hop_end) ? 2 : 1) * (H / 32);
+      for (int i = tid; i < M * lines_per_mic; i += kGenThreads) {
+        const int ch = i / lines_per_mic, ln = i - ch * lines_per_mic;
+        const float* a = p.in + (size_t)s * p.in_stream_stride + (size_t)ch * p.in_mic_stride + (size_t)(t + 2) * H + ln * 32;
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(a));
+      }
+    }
+    constexpr int kIter = (H + kGenThreads - 1) / kGenThreads;
+    auto pack_load = [&](int ch, float (&fa)[kIter], float (&fb)[kIter], float (&fc)[kIter]) {
       const float* base = p.in + (size_t)s * p.in_stream_stride + (size_t)ch * p.in_mic_stride;
       const float* ha = (t - 1 < 0) ? p.prev_hop + ((size_t)s * M + ch) * H : base + (size_t)(t - 1) * H;
       const float* hb = base + (size_t)t * H;
       const float* hc = two ? base + (size_t)(t + 1) * H : hb;
-      // first half of the frames: (hop t-1, hop t); second half: (hop t, hop t+1); loads of a half are issued together
-      constexpr int kIter = (H + kGenThreads - 1) / kGenThreads;
-      float fa[kIter], fb[kIter], fc[kIter];
 #pragma unroll
       for (int k = 0; k < kIter; k++) {
         const int n = tid + k * kGenThreads;
@@ -521,13 +704,18 @@ __global__ void __launch_bounds__(kGenThreads, 1) frames_kernel_n(const KernelPa
         fb[k] = in ? __ldg(hb + n) : 0.f;
         fc[k] = (in && two) ? __ldg(hc + n) : 0.f;
       }
-#pragma unroll
-      for (int k = 0; k < kIter; k++) {
+    };
+    auto pack_store = [&](int ch, const float (&fa)[kIter], const float (&fb)[kIter], const float (&fc)[kIter]) {
+      static_for<0, kIter>([&](auto kc) {
+        constexpr int k = decltype(kc)::value;
         const int n = tid + k * kGenThreads;
-        if ((H % kGenThreads != 0) && n >= H) continue;
+        if ((H % kGenThreads != 0) && n >= H) return;
         const float b1 = two ? fb[k] : 0.f;
         if constexpr (kPha) {
-          const double w0 = 0.5 * p.win_d[n], w1 = 0.5 * p.win_d[n + H];
+          // 0.5 * sqrt-Hann (util.h:201-211) = 0.5 sin(pi n / N) at n = tid + 256 k and n + N/2 (cosine), by angle addition
+          // from the thread's (sin, cos)(pi tid / N) and compile-time (cos, sin)(pi 256 k / N): no table traffic
+          constexpr double ck = cos64((8192 / NN) * k), sk = sin64((8192 / NN) * k);
+          const double w0 = fma(win_s, ck, win_c * sk), w1 = fma(win_c, ck, -win_s * sk);
           zall[(size_t)ch * NN + swz(n)] = make_double2((double)fa[k] * w0, (double)b1 * w0);
           zall[(size_t)ch * NN + swz(n + H)] = make_double2((double)fb[k] * w1, (double)fc[k] * w1);
         } else {
@@ -535,11 +723,31 @@ __global__ void __launch_bounds__(kGenThreads, 1) frames_kernel_n(const KernelPa
           zall[(size_t)ch * NN + swz(n)] = make_float2(fa[k] * w0, b1 * w0);
           zall[(size_t)ch * NN + swz(n + H)] = make_float2(fb[k] * w1, fc[k] * w1);
         }
-      }
+      });
+    };
+    for (int ch = 0; ch < M; ch += 2) {   // two microphones' loads in flight per round trip
+      float fa0[kIter], fb0[kIter], fc0[kIter], fa1[kIter], fb1[kIter], fc1[kIter];
+      pack_load(ch, fa0, fb0, fc0);
+      if (BF_GEN_PACK_PAIR && ch + 1 < M) pack_load(ch + 1, fa1, fb1, fc1);
+      pack_store(ch, fa0, fb0, fc0);
+      if (!BF_GEN_PACK_PAIR && ch + 1 < M) pack_load(ch + 1, fa1, fb1, fc1);
+      if (ch + 1 < M) pack_store(ch + 1, fa1, fb1, fc1);
     }
     __syncthreads();
-    if constexpr (kPha) block_fft<NN, -1, double2>(zall, M, p.twid_d, tid);
-    else block_fft<NN, -1, float2>(zall, M, tw, tid);
+    BF_PHASE(0);
+    if constexpr (NN == 4096 && BF_GEN_FWD_PIPE) {
+      if (M >= 2) {
+        if constexpr (kPha) block_fft4096_multi<-1, double2>(zall, M, p.twid_d, tid);
+        else block_fft4096_multi<-1, float2>(zall, M, tw, tid);
+      } else {
+        if constexpr (kPha) block_fft<NN, -1, double2>(zall, M, p.twid_d, tid);
+        else block_fft<NN, -1, float2>(zall, M, tw, tid);
+      }
+    } else {
+      if constexpr (kPha) block_fft<NN, -1, double2>(zall, M, p.twid_d, tid);
+      else block_fft<NN, -1, float2>(zall, M, tw, tid);
+    }
+    BF_PHASE(1);
     // ---- per-bin beamformer ----
     if constexpr (ALGO == ALGO_DAS) {
       // das.cpp:60-63 commutes with the frame packing: G[j] = sum_i ceff_i[j] * Z_i[j] over all N bins
@@ -588,13 +796,21 @@ __global__ void __launch_bounds__(kGenThreads, 1) frames_kernel_n(const KernelPa
       }
     }
     __syncthreads();
+    BF_PHASE(2);
+    // the spectra are consumed: their storage is the second buffer of an out-of-place inverse (one barrier per pass)
+#if BF_GEN_INV_OOP
+    float2* res = block_fft_oop<NN, 1, float2>(gbuf, reinterpret_cast<float2*>(zall), tw, tid);
+#else
     block_fft<NN, 1, float2>(gbuf, 1, tw, tid);
+    float2* res = gbuf;
+#endif
+    BF_PHASE(3);
     // ---- synthesis window, overlap-add (util.h:244-253, 301-302), optional smoother ----
     float* o0 = p.out + (size_t)s * p.out_stream_stride + (size_t)t * H;
     const int S1 = kSmooth ? p.smooth_size - 1 : 0;
     for (int n = tid; n < H; n += kGenThreads) {
       const float w0 = __ldg(win + n) * p.out_scale, w1 = __ldg(win + n + H) * p.out_scale;
-      const float2 a = gbuf[swz(n)], b = gbuf[swz(n + H)];
+      const float2 a = res[swz(n)], b = res[swz(n + H)];
       const float r0 = sc.tail[n] + a.x * w0;
       if (kSmooth) sc.ola[S1 + n] = r0; else o0[n] = r0;
       if (two) {
@@ -605,6 +821,7 @@ __global__ void __launch_bounds__(kGenThreads, 1) frames_kernel_n(const KernelPa
         sc.tail[n] = b.x * w1;
       }
     }
+    BF_PHASE(4);
     if (kSmooth) {
       // phasempf.cpp:78-83,122-130,331-334: every output sample becomes the mean of the last smooth_size OLA samples
       __syncthreads();
@@ -622,7 +839,14 @@ __global__ void __launch_bounds__(kGenThreads, 1) frames_kernel_n(const KernelPa
       if (tid < S1) sc.ola[tid] = keep;
     }
     __syncthreads();
+    BF_PHASE(5);
   }
+#ifdef BF_PHASE_TIMERS
+  if (p.debug == 1 && blockIdx.x == 0 && tid == 0)
+    printf("frames_kernel_n phases (clk/pair): pack %lld | fwd fft %lld | bins %lld | inv fft %lld | ola %lld | smoother %lld\n", ph_clk[0] / npairs,
+           ph_clk[1] / npairs, ph_clk[2] / npairs, ph_clk[3] / npairs, ph_clk[4] / npairs, ph_clk[5] / npairs);
+#endif
+#undef BF_PHASE
   for (int i = tid; i < H; i += kGenThreads) p.tail[(size_t)s * H + i] = sc.tail[i];
   if (kSmooth)
     for (int i = tid; i < p.smooth_size - 1; i += kGenThreads) p.smooth_hist[(size_t)s * 64 + i] = sc.ola[i];
