@@ -29,14 +29,11 @@
 #include "warp_fft1024.cuh"
 
 // tuning switches (profiling builds override them with -D)
-#ifndef BF_GEN_FWD_PIPE
-#define BF_GEN_FWD_PIPE 0
-#endif
-#ifndef BF_GEN_INV_OOP
-#define BF_GEN_INV_OOP 1
-#endif
 #ifndef BF_GEN_PACK_PAIR
 #define BF_GEN_PACK_PAIR 0
+#endif
+#ifndef BF_GEN_U
+#define BF_GEN_U 2
 #endif
 #ifndef BF_GEN_PREFETCH
 #define BF_GEN_PREFETCH 1
@@ -198,30 +195,23 @@ __device__ __forceinline__ V* block_fft_oop(V* a, V* b, const V* __restrict__ tw
   }
 }
 
-// In-place 4096-point transforms of nfft >= 2 arrays, software-pipelined across the arrays: the step order is
-// (pass 0: f = 0..nfft-1), (pass 1: ...), (pass 2: ...); a step's results are written AFTER the next barrier, together
-// with the next step's reads (which touch another array, or this array one full barrier after its last write), so every
-// step costs one barrier and its stores overlap the next step's loads.  One step = all 256 threads (4096 / 16 tasks).
-template <int DIR, typename V>
-__device__ __forceinline__ void block_fft4096_multi(V* z, int nfft, const V* __restrict__ tw, int tid) {
-  typedef Step<4096, 16, DIR, V> S;
-  static_assert(S::per == kGenThreads, "one step per transform");
-  V v[16];
-  const int steps = 3 * nfft;
-  int f = 0, sh = 0, pf = 0, psh = 0;   // current and previous (array, pass shift)
-#pragma unroll 1
-  for (int i = 0; i <= steps; i++) {
-    if (i > 0) {
-      __syncthreads();
-      S::store(z + (size_t)pf * 4096, tid, psh, v);
-    }
-    if (i < steps) {
-      S::load(z + (size_t)f * 4096, tw, tid, sh, v);
-      pf = f; psh = sh;
-      if (++f == nfft) { f = 0; sh += 4; }
-    }
-  }
-  __syncthreads();
+// ---- out-of-line entry points ----
+// Each heavy stage of the frame-pair loop is its own (non-inlined) function: ptxas then allocates registers per stage
+// instead of across the whole loop (inlined, the stages' live ranges pushed the FP64 radix-16 butterflies into spills
+// and the stage time moved by 50 % from build to build).  Buffers are named by their byte offset in the dynamic
+// shared-memory window, so the accesses stay LDS/STS.
+extern __shared__ __align__(16) unsigned char gen_smem_raw[];
+
+template <int NN, int DIR, typename V>
+__device__ __noinline__ void block_fft_fn(unsigned z_off, int nfft, const V* __restrict__ tw, int tid) {
+  block_fft<NN, DIR, V>(reinterpret_cast<V*>(gen_smem_raw + z_off), nfft, tw, tid);
+}
+// returns the byte offset of the buffer that holds the result
+template <int NN, int DIR, typename V>
+__device__ __noinline__ unsigned block_fft_oop_fn(unsigned a_off, unsigned b_off, const V* __restrict__ tw, int tid) {
+  V* a = reinterpret_cast<V*>(gen_smem_raw + a_off);
+  V* r = block_fft_oop<NN, DIR, V>(a, reinterpret_cast<V*>(gen_smem_raw + b_off), tw, tid);
+  return r == a ? a_off : b_off;
 }
 
 // X_i[j] of frame f from the packed half-scaled double spectrum Z = FFT(0.5*w*(x_t + i x_{t+1}))
@@ -396,8 +386,10 @@ __device__ __forceinline__ void phase_pair_n(const KernelParams& p, int s, int t
 // "< min_phase" is the sign of sin(thr)*Re(u) - cos(thr)*|Im(u)| (0 < thr < pi) and needs no arctangent; results within
 // FP32 rounding of the threshold are re-decided in double from the same double spectra (phase_decide_d).
 template <int ALGO, int NN, int MM>
-__device__ __forceinline__ void phase_pair_fused(const KernelParams& p, int s, int t, bool two, const double2* zall, float2* gbuf,
-                                                 int& cur_L, int& first_L, int tid, float sin_thr, float cos_thr) {
+__device__ __forceinline__ void phase_pair_fused(const KernelParams& p, int s, int t, bool two, unsigned g_off, int& cur_L, int& first_L,
+                                                 int tid, float sin_thr, float cos_thr) {
+  const double2* zall = reinterpret_cast<const double2*>(gen_smem_raw);
+  float2* gbuf = reinterpret_cast<float2*>(gen_smem_raw + g_off);
   constexpr int H = NN / 2, L = NN / 2 + 2;
   constexpr bool kGate = (ALGO == ALGO_PHASE);
   constexpr bool kMpf = (ALGO == ALGO_PHASEMPF);
@@ -573,9 +565,9 @@ __device__ __forceinline__ void phase_pair_fused(const KernelParams& p, int s, i
   };
 
   // Thread tid takes bins tid, tid + T, ..., U per trip.  Bin 0 has no decision (phase.cpp:87, SURVEY B-5), so its
-  // thread takes the Nyquist bin instead; the pseudo-bin N/2+1 is evaluated in one extra trip by the thread that owns
-  // bin N/2-1 (same code, no second copy in the instruction stream) and folded into what that thread wrote for N/2-1.
-  constexpr int U = 2;
+  // thread takes the Nyquist bin instead; the pseudo-bin N/2+1 rides in an extra slot of the thread that owns bin
+  // N/2-1 (last trip) and is folded into it: Yh = (Y[N/2-1] + conj(Y[N/2+1])) / 2.
+  constexpr int U = BF_GEN_U;
   constexpr int kTrips = (H + U * kGenThreads - 1) / (U * kGenThreads);
   if (tid == 0) {
     float2 g0 = make_float2(0.f, 0.f);
@@ -588,44 +580,37 @@ __device__ __forceinline__ void phase_pair_fused(const KernelParams& p, int s, i
       for (int f = 0; f < nf; f++) p.capture[(size_t)s * p.capture_stream_stride + (size_t)(t + f) * NN] = 0;
   }
 #pragma unroll 1
-  for (int trip = 0; trip <= kTrips; trip++) {
-    int lu[U];
-    bool on[U];
-    Bin B[U];
-    float2 y0[U], y1[U];
+  for (int trip = 0; trip < kTrips; trip++) {
+    int lu[U + 1];
+    bool on[U + 1];
+    Bin B[U + 1];
+    float2 y0[U + 1], y1[U + 1];
+    on[U] = false; lu[U] = L - 1;
 #pragma unroll
     for (int u = 0; u < U; u++) {
       lu[u] = tid + (trip * U + u) * kGenThreads;
-      on[u] = trip < kTrips && lu[u] < H;
+      on[u] = lu[u] < H;
       if (!on[u]) lu[u] = 1;
       if (lu[u] == 0) lu[u] = H;
+      if (lu[u] == H - 1) on[U] = true;
     }
-    if (trip == kTrips && tid == ((H - 1) % kGenThreads)) { on[0] = true; lu[0] = L - 1; }
-    bool any = false;
-#pragma unroll
-    for (int u = 0; u < U; u++) any |= on[u];
-    if (!any) continue;
 #pragma unroll
     for (int u = 0; u < U; u++) stage_a(lu[u], B[u]);
+    if (on[U]) stage_a(lu[U], B[U]);
 #pragma unroll
-    for (int u = 0; u < U; u++)
+    for (int u = 0; u <= U; u++)
       if (on[u]) stage_b(lu[u], B[u]);
 #pragma unroll
-    for (int u = 0; u < U; u++)
+    for (int u = 0; u <= U; u++)
       if (on[u]) stage_c(lu[u], B[u], y0[u], y1[u]);
 #pragma unroll
     for (int u = 0; u < U; u++) {
       if (!on[u]) continue;
-      int l = lu[u];
+      const int l = lu[u];
       float2 a0 = y0[u], a1 = y1[u];
-      if (l == L - 1) {
-        // Hermitian part of the asymmetric pair (N/2-1, N/2+1): Yh = (Y[N/2-1] + conj(Y[N/2+1])) / 2; Y[N/2-1] of both
-        // frames is recovered from this thread's own earlier stores
-        l = H - 1;
-        const float2 g = gbuf[swz(l)], g2 = gbuf[swz(NN - l)];
-        const float2 b0 = make_float2(0.5f * (g.x + g2.x), 0.5f * (g.y - g2.y)), b1 = make_float2(0.5f * (g.y + g2.y), 0.5f * (g2.x - g.x));
-        a0 = make_float2(0.5f * (b0.x + a0.x), 0.5f * (b0.y - a0.y));
-        a1 = make_float2(0.5f * (b1.x + a1.x), 0.5f * (b1.y - a1.y));
+      if (l == H - 1) {
+        a0 = make_float2(0.5f * (a0.x + y0[U].x), 0.5f * (a0.y - y0[U].y));
+        a1 = make_float2(0.5f * (a1.x + y1[U].x), 0.5f * (a1.y - y1[U].y));
       }
       if (l == H) { a0.y = 0.f; a1.y = 0.f; }   // Re(): self-conjugate bin
       gbuf[swz(l)] = make_float2(a0.x - a1.y, a0.y + a1.x);                          // Yh_t + i Yh_{t+1}
@@ -636,14 +621,15 @@ __device__ __forceinline__ void phase_pair_fused(const KernelParams& p, int s, i
 
 
 template <int ALGO, int NN>
-__global__ void __launch_bounds__(kGenThreads, 1) frames_kernel_n(const KernelParams p) {
+__global__ void __launch_bounds__(kGenThreads, 1) frames_kernel_n(const __grid_constant__ KernelParams p) {
   constexpr int H = NN / 2, L = NN / 2 + 2;
   constexpr bool kPha = (ALGO == ALGO_PHASE || ALGO == ALGO_PHASEMPF);
   constexpr bool kSmooth = (ALGO == ALGO_PHASEMPF);
   typedef typename std::conditional<kPha, double2, float2>::type ZV;   // forward spectra: double for the phase masks
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  unsigned char* smem_raw = gen_smem_raw;
   ZV* zall = reinterpret_cast<ZV*>(smem_raw);                            // [M][NN]
   float2* gbuf = reinterpret_cast<float2*>(zall + (size_t)p.M * NN);     // [NN]
+  const unsigned g_off = (unsigned)((size_t)p.M * NN * sizeof(ZV));
   GenScratch<NN>& sc = *reinterpret_cast<GenScratch<NN>*>(gbuf + NN);
   const int tid = threadIdx.x;
   const int M = p.M;
@@ -735,18 +721,8 @@ __global__ void __launch_bounds__(kGenThreads, 1) frames_kernel_n(const KernelPa
     }
     __syncthreads();
     BF_PHASE(0);
-    if constexpr (NN == 4096 && BF_GEN_FWD_PIPE) {
-      if (M >= 2) {
-        if constexpr (kPha) block_fft4096_multi<-1, double2>(zall, M, p.twid_d, tid);
-        else block_fft4096_multi<-1, float2>(zall, M, tw, tid);
-      } else {
-        if constexpr (kPha) block_fft<NN, -1, double2>(zall, M, p.twid_d, tid);
-        else block_fft<NN, -1, float2>(zall, M, tw, tid);
-      }
-    } else {
-      if constexpr (kPha) block_fft<NN, -1, double2>(zall, M, p.twid_d, tid);
-      else block_fft<NN, -1, float2>(zall, M, tw, tid);
-    }
+    if constexpr (kPha) block_fft_fn<NN, -1, double2>(0u, M, p.twid_d, tid);
+    else block_fft_fn<NN, -1, float2>(0u, M, tw, tid);
     BF_PHASE(1);
     // ---- per-bin beamformer ----
     if constexpr (ALGO == ALGO_DAS) {
@@ -763,9 +739,9 @@ __global__ void __launch_bounds__(kGenThreads, 1) frames_kernel_n(const KernelPa
       }
     } else {
       if (M >= 2 && M <= 4) {
-        if (M == 2) phase_pair_fused<ALGO, NN, 2>(p, s, t, two, zall, gbuf, cur_L, first_L, tid, sin_thr, cos_thr);
-        else if (M == 3) phase_pair_fused<ALGO, NN, 3>(p, s, t, two, zall, gbuf, cur_L, first_L, tid, sin_thr, cos_thr);
-        else phase_pair_fused<ALGO, NN, 4>(p, s, t, two, zall, gbuf, cur_L, first_L, tid, sin_thr, cos_thr);
+        if (M == 2) phase_pair_fused<ALGO, NN, 2>(p, s, t, two, g_off, cur_L, first_L, tid, sin_thr, cos_thr);
+        else if (M == 3) phase_pair_fused<ALGO, NN, 3>(p, s, t, two, g_off, cur_L, first_L, tid, sin_thr, cos_thr);
+        else phase_pair_fused<ALGO, NN, 4>(p, s, t, two, g_off, cur_L, first_L, tid, sin_thr, cos_thr);
       } else {
             phase_pair_n<ALGO, NN>(p, s, t, two, zall, sc, cur_L, first_L, tid);
       for (int l = tid; l <= H; l += kGenThreads) {   // Hermitian assembly of G = Yh_t + i Yh_{t+1}
@@ -798,12 +774,7 @@ __global__ void __launch_bounds__(kGenThreads, 1) frames_kernel_n(const KernelPa
     __syncthreads();
     BF_PHASE(2);
     // the spectra are consumed: their storage is the second buffer of an out-of-place inverse (one barrier per pass)
-#if BF_GEN_INV_OOP
-    float2* res = block_fft_oop<NN, 1, float2>(gbuf, reinterpret_cast<float2*>(zall), tw, tid);
-#else
-    block_fft<NN, 1, float2>(gbuf, 1, tw, tid);
-    float2* res = gbuf;
-#endif
+    const float2* res = reinterpret_cast<const float2*>(smem_raw + block_fft_oop_fn<NN, 1, float2>(g_off, 0u, tw, tid));
     BF_PHASE(3);
     // ---- synthesis window, overlap-add (util.h:244-253, 301-302), optional smoother ----
     float* o0 = p.out + (size_t)s * p.out_stream_stride + (size_t)t * H;
