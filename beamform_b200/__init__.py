@@ -60,6 +60,8 @@ GEOMETRIES = {
     "aira3": [(0.000, 0.000), (0.000, -0.180), (-0.156, -0.090)],
     "binaural": [(0.000, 0.000), (0.000, -0.342)],
     "circ8": [(0.10 * np.cos(2 * np.pi * k / 8), 0.10 * np.sin(2 * np.pi * k / 8)) for k in range(8)],
+    "circ12": [(0.12 * np.cos(2 * np.pi * k / 12), 0.12 * np.sin(2 * np.pi * k / 12)) for k in range(12)],
+    "circ16": [(0.15 * np.cos(2 * np.pi * k / 16), 0.15 * np.sin(2 * np.pi * k / 16)) for k in range(16)],
     "grid64": [(0.04 * (k % 8), 0.04 * (k // 8)) for k in range(64)],
 }
 

@@ -32,6 +32,8 @@ bool sel_pairs_supported(const KernelParams& p, int algo);
 cudaError_t launch_sel_pairs(int algo, const KernelParams& p, cudaStream_t st);
 cudaError_t launch_frames_kernel_n(int algo, const KernelParams& p, cudaStream_t st);
 size_t frames_kernel_n_smem(int N, int M, int algo);
+cudaError_t launch_frames_kernel_sel(int algo, const KernelParams& p, cudaStream_t st);
+size_t frames_kernel_sel_smem(int N, int M);
 cudaError_t launch_srp(const KernelParams& p, float2* xs, const double* tau, const double* freqs_l, float* maps, int D, int n_hops,
                        cudaStream_t st);
 }   // namespace bf
@@ -358,10 +360,16 @@ extern "C" int bf_create(bf_handle** out, const bf_config* cfg, uint32_t n_strea
   if (n_streams < 1) return fail(BF_ERR_INVALID, "bf_create: n_streams must be >= 1");
   if (cfg->hop != 256 && cfg->hop != 512 && cfg->hop != 1024 && cfg->hop != 2048)
     return fail(BF_ERR_INVALID, "bf_create: hop (JACK period) must be 256, 512, 1024 or 2048 (512- to 4096-point frames)");
-  if (cfg->hop != 512) {
-    if (cfg->algo == BF_ALGO_MVDR || cfg->algo == BF_ALGO_LCMV || cfg->algo == BF_ALGO_GSS)
-      return fail(BF_ERR_INVALID, "bf_create: mvdr/lcmv/gss are built for 1024-point frames (hop 512) only");
-    if (bf::frames_kernel_n_smem(2 * (int)cfg->hop, cfg->n_mics, cfg->algo) > 232448)
+  {
+    const bool sel = cfg->algo == BF_ALGO_MVDR || cfg->algo == BF_ALGO_LCMV || cfg->algo == BF_ALGO_GSS;
+    // 1024-point frames with <= 8 microphones run on the register-resident kernels; everything else keeps the
+    // spectra of one frame pair in shared memory
+    if (sel && (cfg->hop != 512 || cfg->n_mics > 8) && !(cfg->algo == BF_ALGO_GSS && cfg->hop == 512)) {
+      if (cfg->n_mics > 16) return fail(BF_ERR_INVALID, "bf_create: mvdr/lcmv (and gss at this frame size) support at most 16 microphones");
+      if (bf::frames_kernel_sel_smem(2 * (int)cfg->hop, cfg->n_mics) > 232448)
+        return fail(BF_ERR_INVALID, "bf_create: too many microphones for this frame size (spectra must fit 227 KB of shared memory)");
+    }
+    if (!sel && cfg->hop != 512 && bf::frames_kernel_n_smem(2 * (int)cfg->hop, cfg->n_mics, cfg->algo) > 232448)
       return fail(BF_ERR_INVALID, "bf_create: too many microphones for this frame size (spectra must fit 227 KB of shared memory)");
   }
   if (cfg->algo < 0 || cfg->algo > 5) return fail(BF_ERR_INVALID, "bf_create: unknown algo");
@@ -437,7 +445,6 @@ extern "C" int bf_create(bf_handle** out, const bf_config* cfg, uint32_t n_strea
       cudaMemset(h->d_smooth_hist, 0, sizeof(float) * h->B * 64);     // phasempf.cpp:510 calloc
     }
     if (sel_algo || pha_algo) {
-      if ((cfg->algo == BF_ALGO_MVDR || cfg->algo == BF_ALGO_LCMV) && h->M > 8) { bf_destroy(h); return fail(BF_ERR_INVALID, "bf_create: mvdr/lcmv support at most 8 microphones in this build"); }
       if (cfg->past_windows < 1) { bf_destroy(h); return fail(BF_ERR_INVALID, "bf_create: past_windows must be >= 1"); }
       std::vector<double> win(h->N);
       std::vector<double2> twd(h->N);
@@ -656,7 +663,11 @@ static int run_segment(bf_handle* h, const float* in, size_t ss, size_t ms, floa
   }
   static const bool force_generic = getenv("BF_GENERIC") != nullptr;   // debug: cross-check the generic kernel at N = 1024
   const bool gen_algo = h->cfg.algo == BF_ALGO_DAS || h->cfg.algo == BF_ALGO_PHASE || h->cfg.algo == BF_ALGO_PHASEMPF;
-  if (h->N != 1024 || (force_generic && gen_algo)) CUDA_TRY(bf::launch_frames_kernel_n(h->cfg.algo, p, st));
+  static const bool force_sel_generic = getenv("BF_SEL_GENERIC") != nullptr;   // debug: cross-check the general gated kernel
+  const bool sel_algo = h->cfg.algo == BF_ALGO_MVDR || h->cfg.algo == BF_ALGO_LCMV || h->cfg.algo == BF_ALGO_GSS;
+  if (sel_algo && (h->N != 1024 || force_sel_generic || (h->M > 8 && h->cfg.algo != BF_ALGO_GSS)))
+    CUDA_TRY(bf::launch_frames_kernel_sel(h->cfg.algo, p, st));
+  else if (h->N != 1024 || (force_generic && gen_algo)) CUDA_TRY(bf::launch_frames_kernel_n(h->cfg.algo, p, st));
   else if (h->cfg.algo == BF_ALGO_DAS && bf::das_pairs_supported(p)) CUDA_TRY(bf::launch_das_pairs(p, st, h->sm_count));
   else if (bf::sel_pairs_supported(p, h->cfg.algo)) CUDA_TRY(bf::launch_sel_pairs(h->cfg.algo, p, st));
   else CUDA_TRY(bf::launch_frames_kernel_1024(h->cfg.algo, p, st));

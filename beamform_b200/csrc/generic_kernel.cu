@@ -27,6 +27,7 @@
 #include "fft_reg.cuh"
 #include "fft_reg_d.cuh"
 #include "warp_fft1024.cuh"
+#include "phase_b_select.cuh"
 
 // tuning switches (profiling builds override them with -D)
 #ifndef BF_GEN_PACK_PAIR
@@ -821,6 +822,418 @@ __global__ void __launch_bounds__(kGenThreads, 1) frames_kernel_n(const __grid_c
   for (int i = tid; i < H; i += kGenThreads) p.tail[(size_t)s * H + i] = sc.tail[i];
   if (kSmooth)
     for (int i = tid; i < p.smooth_size - 1; i += kGenThreads) p.smooth_hist[(size_t)s * 64 + i] = sc.ola[i];
+}
+
+// =====================================================================================================================
+// Magnitude-gated nodes (mvdr / lcmv / gss) at any supported frame size and up to 16 microphones.
+//
+//   reference path replaced: apply_weights of mvdr.cpp:62-115, lcmv.cpp:88-140, gss.cpp:96-156 (+ framing / OLA as above).
+//
+// The 1024-point, M <= 8 configurations run on sel_kernel.cu (register-resident 8x8 solves).  This kernel covers the
+// rest of the parameter space with the same numerics contract: FP32 spectra, magnitude gate with a guard band whose
+// bins are re-decided from an exact double DFT (bit-exact selected-bin set), solves in double with the matrices in
+// per-thread local memory (run-time M), history ring in the layout of sel_kernel.cu ([B][P+2][M][Lsel], bin fastest).
+// =====================================================================================================================
+constexpr int kSelMaxM = 16;
+
+template <int NN>
+struct SelGenScratch {
+  static constexpr int L = NN / 2 + 2;
+  float2 y[2][L];
+  unsigned char flag[2][L];
+  unsigned short items[2 * L];
+  unsigned short recheck[2 * L];
+  int n_items, n_recheck;
+  float esq[2][kSelMaxM];   // windowed frame energies per microphone (scale of the FP32 transform's absolute error)
+  int nonfinite[2];
+  float tail[NN / 2];
+};
+
+template <int NN>
+__device__ __forceinline__ void unpack2_n(const float2* z, int l, float2& x0, float2& x1) {
+  constexpr int L = NN / 2 + 2;
+  const int j = (l == L - 1) ? NN / 2 - 1 : l;   // pseudo-bin: conj of bin N/2-1 (SURVEY B-4)
+  const float2 a = z[swz(j)], b = z[swz((NN - j) & (NN - 1))];
+  x0 = make_float2(a.x + b.x, a.y - b.y);    // Z[j] + conj(Z[N-j])
+  x1 = make_float2(a.y + b.y, b.x - a.x);    // -i (Z[j] - conj(Z[N-j]))
+  if (l == L - 1) { x0.y = -x0.y; x1.y = -x1.y; }
+}
+
+// FP64 re-decision of the magnitude gate for one (bin, frame): exact double DFT of that bin (mvdr.cpp:79-85), one warp.
+template <int NN>
+__device__ __noinline__ bool gate_fp64_n(const KernelParams& p, int s, int t, int l, int f, int lane) {
+  constexpr int H = NN / 2, L = NN / 2 + 2;
+  const int j = (l == L - 1) ? H + 1 : l;
+  double stat = 0.0;
+  for (int ch = 0; ch < p.M; ch++) {
+    const int hf = t + f;
+    const float* base = p.in + (size_t)s * p.in_stream_stride + (size_t)ch * p.in_mic_stride;
+    const float* h0 = (hf - 1 < 0) ? p.prev_hop + ((size_t)s * p.M + ch) * H : base + (size_t)(hf - 1) * H;
+    const float* h1 = base + (size_t)hf * H;
+    double re = 0.0, im = 0.0;
+    for (int n = lane; n < NN; n += 32) {
+      const double xv = (double)(n < H ? h0[n] : h1[n - H]) * p.win_d[n];
+      const double2 w = p.twid_d[(j * n) & (NN - 1)];
+      re = fma(xv, w.x, re);
+      im = fma(xv, w.y, im);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      re += __shfl_xor_sync(0xffffffffu, re, o);
+      im += __shfl_xor_sync(0xffffffffu, im, o);
+    }
+    stat += hypot(re, im);
+  }
+  stat /= (double)((unsigned)p.M * (unsigned)NN);
+  return stat > p.thr_mag_d;
+}
+
+// One selected (bin, frame) of mvdr / lcmv in double, run-time M <= 16 and C <= 8 (mvdr: C = 1).
+//   R = (P P^H) .* whiteR (mvdr.cpp:87, :239-243) = L L^H;  V = L^{-1} C, u = L^{-1} x, G = V^H V, b = V^H u;
+//   y = g^H b with G g = e_0  (lcmv.cpp:111-119; for C = 1 this is mvdr.cpp:86-94: y = z^H u / z^H z).
+__device__ __noinline__ float2 sel_item_d(const KernelParams& p, const float2* ring_l, int slot0, const float2* x, const float2* steer_l) {
+  const int M = p.M, C = p.C, D = p.ring_depth;
+  const size_t mic_stride = (size_t)p.Lsel, slot_stride = (size_t)M * p.Lsel;
+  double2 A[kSelMaxM][kSelMaxM];   // lower triangle: covariance, then its Cholesky factor
+  for (int i = 0; i < M; i++)
+    for (int j = 0; j <= i; j++) A[i][j] = make_double2(0.0, 0.0);
+  int slot = slot0;
+  for (int k = 0; k < p.P; k++) {
+    double2 h[kSelMaxM];
+    const float2* src = ring_l + (size_t)slot * slot_stride;
+    if (++slot == D) slot = 0;
+    for (int i = 0; i < M; i++) { const float2 v = src[(size_t)i * mic_stride]; h[i] = make_double2((double)v.x, (double)v.y); }
+    for (int i = 0; i < M; i++)
+      for (int j = 0; j <= i; j++) {   // h_i conj(h_j)
+        A[i][j].x = fma(h[i].x, h[j].x, fma(h[i].y, h[j].y, A[i][j].x));
+        A[i][j].y = fma(h[i].y, h[j].x, fma(-h[i].x, h[j].y, A[i][j].y));
+      }
+  }
+  double invd[kSelMaxM];
+  for (int j = 0; j < M; j++) {
+    double d = A[j][j].x * 1.001;   // whiteR diagonal (mvdr.cpp:242)
+    for (int k = 0; k < j; k++) d = fma(-A[j][k].x, A[j][k].x, fma(-A[j][k].y, A[j][k].y, d));
+    const double inv = 1.0 / sqrt(d);
+    invd[j] = inv;
+    for (int i = j + 1; i < M; i++) {
+      double2 acc = A[i][j];
+      for (int k = 0; k < j; k++) {   // acc -= L[i][k] conj(L[j][k])
+        const double2 a = A[i][k], b = A[j][k];
+        acc.x = fma(-a.x, b.x, fma(-a.y, b.y, acc.x));
+        acc.y = fma(-a.y, b.x, fma(a.x, b.y, acc.y));
+      }
+      A[i][j] = make_double2(acc.x * inv, acc.y * inv);
+    }
+  }
+  auto fwd = [&](double2* v) {   // v <- L^{-1} v
+    for (int i = 0; i < M; i++) {
+      double2 acc = v[i];
+      for (int k = 0; k < i; k++) {
+        const double2 l = A[i][k];
+        acc.x = fma(-l.x, v[k].x, fma(l.y, v[k].y, acc.x));
+        acc.y = fma(-l.x, v[k].y, fma(-l.y, v[k].x, acc.y));
+      }
+      v[i] = make_double2(acc.x * invd[i], acc.y * invd[i]);
+    }
+  };
+  auto dotc = [&](const double2* a, const double2* b) {   // sum conj(a_i) b_i
+    double2 r = make_double2(0.0, 0.0);
+    for (int i = 0; i < M; i++) {
+      r.x = fma(a[i].x, b[i].x, fma(a[i].y, b[i].y, r.x));
+      r.y = fma(a[i].x, b[i].y, fma(-a[i].y, b[i].x, r.y));
+    }
+    return r;
+  };
+  double2 u[kSelMaxM];
+  for (int i = 0; i < M; i++) u[i] = make_double2((double)x[i].x, (double)x[i].y);
+  fwd(u);
+  double2 V[kMaxC][kSelMaxM], G[kMaxC][kMaxC], b[kMaxC];
+  for (int c = 0; c < C; c++) {
+    for (int i = 0; i < M; i++) { const float2 a = steer_l[(size_t)c * M + i]; V[c][i] = make_double2((double)a.x, (double)a.y); }
+    fwd(V[c]);
+    b[c] = dotc(V[c], u);
+    for (int c2 = 0; c2 <= c; c2++) G[c][c2] = dotc(V[c], V[c2]);
+  }
+  if (C == 1) {   // mvdr.cpp:90-94
+    const double den = G[0][0].x;
+    return make_float2((float)(b[0].x / den), (float)(b[0].y / den));
+  }
+  double gd[kMaxC];
+  for (int j = 0; j < C; j++) {   // Cholesky of G
+    double d = G[j][j].x;
+    for (int k = 0; k < j; k++) d -= G[j][k].x * G[j][k].x + G[j][k].y * G[j][k].y;
+    gd[j] = 1.0 / sqrt(d);
+    for (int i = j + 1; i < C; i++) {
+      double2 acc = G[i][j];
+      for (int k = 0; k < j; k++) {
+        const double2 a = G[i][k], bb = G[j][k];
+        acc.x -= a.x * bb.x + a.y * bb.y;
+        acc.y -= a.y * bb.x - a.x * bb.y;
+      }
+      G[i][j] = make_double2(acc.x * gd[j], acc.y * gd[j]);
+    }
+  }
+  double2 q[kMaxC], g[kMaxC];
+  for (int i = 0; i < C; i++) {   // q = Lg^{-1} e0
+    double2 acc = make_double2(i == 0 ? 1.0 : 0.0, 0.0);
+    for (int k = 0; k < i; k++) {
+      const double2 l = G[i][k];
+      acc.x -= l.x * q[k].x - l.y * q[k].y;
+      acc.y -= l.x * q[k].y + l.y * q[k].x;
+    }
+    q[i] = make_double2(acc.x * gd[i], acc.y * gd[i]);
+  }
+  for (int i = C - 1; i >= 0; i--) {   // g = Lg^{-H} q
+    double2 acc = q[i];
+    for (int k = i + 1; k < C; k++) {
+      const double2 l = G[k][i];
+      acc.x -= l.x * g[k].x + l.y * g[k].y;
+      acc.y -= l.x * g[k].y - l.y * g[k].x;
+    }
+    g[i] = make_double2(acc.x * gd[i], acc.y * gd[i]);
+  }
+  double2 yv = make_double2(0.0, 0.0);   // y = g^H b
+  for (int c = 0; c < C; c++) {
+    yv.x += g[c].x * b[c].x + g[c].y * b[c].y;
+    yv.y += g[c].x * b[c].y - g[c].y * b[c].x;
+  }
+  return make_float2((float)yv.x, (float)yv.y);
+}
+
+template <int ALGO, int NN>
+__global__ void __launch_bounds__(kGenThreads, 1) frames_kernel_sel(const __grid_constant__ KernelParams p) {
+  constexpr int H = NN / 2, L = NN / 2 + 2;
+  unsigned char* smem_raw = gen_smem_raw;
+  float2* zall = reinterpret_cast<float2*>(smem_raw);                     // [M][NN] packed spectra
+  float2* gbuf = zall + (size_t)p.M * NN;                                  // [NN]
+  SelGenScratch<NN>& sc = *reinterpret_cast<SelGenScratch<NN>*>(gbuf + NN);
+  const unsigned g_off = (unsigned)((size_t)p.M * NN * sizeof(float2));
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int M = p.M, D = p.ring_depth;
+  const int s = blockIdx.x + p.stream_begin;
+  const float2* tw = p.twid_f;
+  const float* win = p.win_f;
+
+  for (int i = tid; i < H; i += kGenThreads) sc.tail[i] = p.tail[(size_t)s * H + i];
+  __syncthreads();
+  const int nh = p.hop_end - p.hop_begin;
+  const int npairs = (nh + 1) >> 1;
+  for (int ip = 0; ip < npairs; ip++) {
+    const int t = p.hop_begin + 2 * ip;
+    const bool two = t + 1 < p.hop_end;
+    const int nf = two ? 2 : 1;
+    if (tid < 2 * kSelMaxM) (&sc.esq[0][0])[tid] = 0.f;
+    if (tid == 0) { sc.n_items = 0; sc.n_recheck = 0; sc.nonfinite[0] = 0; sc.nonfinite[1] = 0; }
+    __syncthreads();
+    // ---- window + pack (util.h:217-242), frame energies ----
+    for (int ch = 0; ch < M; ch++) {
+      const float* base = p.in + (size_t)s * p.in_stream_stride + (size_t)ch * p.in_mic_stride;
+      const float* ha = (t - 1 < 0) ? p.prev_hop + ((size_t)s * M + ch) * H : base + (size_t)(t - 1) * H;
+      const float* hb = base + (size_t)t * H;
+      const float* hc = two ? base + (size_t)(t + 1) * H : hb;
+      float e0 = 0.f, e1 = 0.f;
+      for (int n = tid; n < H; n += kGenThreads) {
+        const float a = __ldg(ha + n), b = __ldg(hb + n), c = two ? __ldg(hc + n) : 0.f;
+        const float w0 = 0.5f * __ldg(win + n), w1 = 0.5f * __ldg(win + n + H);
+        const float2 z0 = make_float2(a * w0, (two ? b : 0.f) * w0), z1 = make_float2(b * w1, c * w1);
+        zall[(size_t)ch * NN + swz(n)] = z0;
+        zall[(size_t)ch * NN + swz(n + H)] = z1;
+        e0 += z0.x * z0.x + z1.x * z1.x;
+        e1 += z0.y * z0.y + z1.y * z1.y;
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) { e0 += __shfl_xor_sync(0xffffffffu, e0, o); e1 += __shfl_xor_sync(0xffffffffu, e1, o); }
+      if (lane == 0) { atomicAdd(&sc.esq[0][ch], e0); atomicAdd(&sc.esq[1][ch], e1); }
+    }
+    __syncthreads();
+    block_fft_fn<NN, -1, float2>(0u, M, tw, tid);
+    const int fr0 = (p.ring_slot0 + (t - p.hop_begin)) % D;   // ring slot of frame t
+    // ---- B1: gate, history append, defaults ----
+    float es0 = 0.f, es1 = 0.f;
+    for (int ch = 0; ch < M; ch++) { es0 += 2.0f * sqrtf(sc.esq[0][ch]); es1 += 2.0f * sqrtf(sc.esq[1][ch]); }
+    const float g0 = 2.0e-5f * es0 + 1.0e-6f * p.thr_mag, g1 = 2.0e-5f * es1 + 1.0e-6f * p.thr_mag;
+    for (int l = tid; l < L; l += kGenThreads) {
+      const bool inb = p.inband[l] != 0 && !(ALGO == ALGO_MVDR && l == 0);
+      if (!inb) {   // out of band: 0 (mvdr.cpp:103), except mvdr's bin 0 which passes microphone 0 through (mvdr.cpp:76)
+        float2 a = make_float2(0.f, 0.f), b = a;
+        if (ALGO == ALGO_MVDR && l == 0) unpack2_n<NN>(zall, 0, a, b);
+        sc.flag[0][l] = 0; sc.flag[1][l] = 0;
+        sc.y[0][l] = a; sc.y[1][l] = b;
+        continue;
+      }
+      float st0 = 0.f, st1 = 0.f;
+      float2 x00 = make_float2(0.f, 0.f), x10 = x00;
+      float2* ring_l = (ALGO != ALGO_GSS) ? p.hist + (size_t)s * D * M * p.Lsel + p.sel_slot[l] : nullptr;
+      const int fs0 = fr0, fs1 = (fr0 + 1 == D) ? 0 : fr0 + 1;
+      for (int ch = 0; ch < M; ch++) {
+        float2 x0, x1;
+        unpack2_n<NN>(zall + (size_t)ch * NN, l, x0, x1);
+        if (ch == 0) { x00 = x0; x10 = x1; }
+        st0 += sqrtf(fmaf(x0.x, x0.x, x0.y * x0.y));
+        st1 += sqrtf(fmaf(x1.x, x1.x, x1.y * x1.y));
+        if (ALGO != ALGO_GSS) {   // mvdr.cpp:99-101: every in-band bin appends every frame
+          ring_l[((size_t)fs0 * M + ch) * p.Lsel] = x0;
+          if (two) ring_l[((size_t)fs1 * M + ch) * p.Lsel] = x1;
+        }
+      }
+      unsigned char f0 = 0, f1 = 0;
+      if (fabsf(st0 - p.thr_mag) <= g0) sc.recheck[atomicAdd(&sc.n_recheck, 1)] = (unsigned short)(l * 2);
+      else if (st0 > p.thr_mag) f0 = 1;
+      if (two) {
+        if (fabsf(st1 - p.thr_mag) <= g1) sc.recheck[atomicAdd(&sc.n_recheck, 1)] = (unsigned short)(l * 2 + 1);
+        else if (st1 > p.thr_mag) f1 = 1;
+      }
+      sc.flag[0][l] = f0; sc.flag[1][l] = f1;
+      sc.y[0][l] = make_float2(0.01f * x00.x, 0.01f * x00.y);   // mvdr.cpp:96 (overwritten when selected)
+      sc.y[1][l] = make_float2(0.01f * x10.x, 0.01f * x10.y);
+    }
+    __syncthreads();
+    // ---- B1b: FP64 re-decision of guarded bins ----
+    for (int q = warp; q < sc.n_recheck; q += kGenThreads / 32) {
+      const int l = sc.recheck[q] >> 1, f = sc.recheck[q] & 1;
+      const bool sel = gate_fp64_n<NN>(p, s, t, l, f, lane);
+      if (lane == 0 && sel) sc.flag[f][l] = 1;
+    }
+    __syncthreads();
+    // ---- work list (ordered: neighbouring threads take neighbouring bins) ----
+    for (int f = 0; f < (ALGO == ALGO_GSS ? 1 : nf); f++)
+      for (int base = 0; base < L; base += kGenThreads) {
+        const int l = base + tid;
+        bool on = false;
+        if (l < L) on = (ALGO == ALGO_GSS) ? ((sc.flag[0][l] | sc.flag[1][l]) != 0) : (sc.flag[f][l] != 0);
+        const unsigned m = __ballot_sync(0xffffffffu, on);
+        int pos = 0;
+        if (lane == 0 && m) pos = atomicAdd(&sc.n_items, __popc(m));
+        pos = __shfl_sync(0xffffffffu, pos, 0);
+        if (on) sc.items[pos + __popc(m & ((1u << lane) - 1u))] = (unsigned short)(l * 2 + f);
+      }
+    __syncthreads();
+    // ---- B2: per-item solves ----
+    for (int q = tid; q < sc.n_items; q += kGenThreads) {
+      const int l = sc.items[q] >> 1, f = sc.items[q] & 1;
+      const float2* steer_l = p.steer + (size_t)l * p.C * M;
+      float2 x[kSelMaxM];
+      if (ALGO == ALGO_GSS) {
+        float2* Wg = p.gss_w + (size_t)s * 8 * M * p.Lsel + p.sel_slot[l];   // [B][8][M][Lsel]
+        for (int ff = 0; ff < nf; ff++) {
+          if (!sc.flag[ff][l]) continue;
+          for (int ch = 0; ch < M; ch++) {
+            float2 a, b;
+            unpack2_n<NN>(zall + (size_t)ch * NN, l, a, b);
+            x[ch] = ff ? b : a;
+          }
+          sc.y[ff][l] = gss_item(p, Wg, (size_t)p.Lsel, x, steer_l);
+        }
+      } else {
+        for (int ch = 0; ch < M; ch++) {
+          float2 a, b;
+          unpack2_n<NN>(zall + (size_t)ch * NN, l, a, b);
+          x[ch] = f ? b : a;
+        }
+        int slot = (fr0 + f - p.P) % D;   // ring slot of frame (t+f) - P
+        if (slot < 0) slot += D;
+        sc.y[f][l] = sel_item_d(p, p.hist + (size_t)s * D * M * p.Lsel + p.sel_slot[l], slot, x, steer_l);
+      }
+    }
+    __syncthreads();
+    // ---- B3: non-finite frames (cold start, SURVEY B-10), Hermitian assembly, diagnostics ----
+    {
+      bool b0 = false, b1 = false;
+      for (int l = tid; l < L; l += kGenThreads) {
+        const float2 y0 = sc.y[0][l], y1 = sc.y[1][l];
+        b0 |= !(isfinite(y0.x) && isfinite(y0.y));
+        b1 |= two && !(isfinite(y1.x) && isfinite(y1.y));
+      }
+      if (b0) sc.nonfinite[0] = 1;
+      if (b1) sc.nonfinite[1] = 1;
+    }
+    __syncthreads();
+    const bool z0 = sc.nonfinite[0] != 0, z1 = sc.nonfinite[1] != 0;
+    for (int l = tid; l < L; l += kGenThreads) {
+      if (l <= H) {
+        float2 y0 = z0 ? make_float2(0.f, 0.f) : sc.y[0][l], y1 = (two && !z1) ? sc.y[1][l] : make_float2(0.f, 0.f);
+        if (l == H - 1) {   // Hermitian part of the asymmetric pair (N/2-1, N/2+1)
+          const float2 p0 = z0 ? make_float2(0.f, 0.f) : sc.y[0][L - 1], p1 = (two && !z1) ? sc.y[1][L - 1] : make_float2(0.f, 0.f);
+          y0 = make_float2(0.5f * (y0.x + p0.x), 0.5f * (y0.y - p0.y));
+          y1 = make_float2(0.5f * (y1.x + p1.x), 0.5f * (y1.y - p1.y));
+        }
+        if (l == 0 || l == H) { y0.y = 0.f; y1.y = 0.f; }
+        gbuf[swz(l)] = make_float2(y0.x - y1.y, y0.y + y1.x);
+        if (l > 0 && l < H) gbuf[swz(NN - l)] = make_float2(y0.x + y1.y, y1.x - y0.y);
+      }
+      if (p.capture) {
+        for (int f = 0; f < nf; f++) {
+          unsigned char* cap = p.capture + (size_t)s * p.capture_stream_stride + (size_t)(t + f) * NN;
+          const unsigned char fl = sc.flag[f][l];
+          if (l <= H) {
+            cap[l] = fl;
+            if (l > 0 && l < H - 1) cap[NN - l] = fl;
+          } else {
+            cap[H + 1] = fl;
+          }
+        }
+      }
+    }
+    __syncthreads();
+    const float2* res = reinterpret_cast<const float2*>(smem_raw + block_fft_oop_fn<NN, 1, float2>(g_off, 0u, tw, tid));
+    // ---- synthesis window, overlap-add (util.h:244-253, 301-302); a poisoned frame turns its samples into NaN ----
+    const float bad0 = z0 ? __int_as_float(0x7fc00000) : 0.f, bad1 = z1 ? __int_as_float(0x7fc00000) : 0.f;
+    float* o0 = p.out + (size_t)s * p.out_stream_stride + (size_t)t * H;
+    for (int n = tid; n < H; n += kGenThreads) {
+      const float w0 = __ldg(win + n) * p.out_scale, w1 = __ldg(win + n + H) * p.out_scale;
+      const float2 a = res[swz(n)], b = res[swz(n + H)];
+      o0[n] = sc.tail[n] + (a.x * w0 + bad0);
+      if (two) {
+        o0[H + n] = (b.x * w1 + bad0) + (a.y * w0 + bad1);
+        sc.tail[n] = b.y * w1 + bad1;
+      } else {
+        sc.tail[n] = b.x * w1 + bad0;
+      }
+    }
+    __syncthreads();
+  }
+  for (int i = tid; i < H; i += kGenThreads) p.tail[(size_t)s * H + i] = sc.tail[i];
+}
+
+template <int NN>
+static size_t sel_gen_smem(int M) { return sizeof(float2) * ((size_t)M + 1) * NN + sizeof(SelGenScratch<NN>) + 16; }
+
+size_t frames_kernel_sel_smem(int N, int M) {
+  switch (N) {
+    case 512: return sel_gen_smem<512>(M);
+    case 1024: return sel_gen_smem<1024>(M);
+    case 2048: return sel_gen_smem<2048>(M);
+    case 4096: return sel_gen_smem<4096>(M);
+  }
+  return ~(size_t)0;
+}
+
+template <int ALGO, int NN>
+static cudaError_t launch_sel_n(const KernelParams& p, cudaStream_t st) {
+  const size_t smem = sel_gen_smem<NN>(p.M);
+  cudaError_t e = cudaFuncSetAttribute(frames_kernel_sel<ALGO, NN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  frames_kernel_sel<ALGO, NN><<<p.n_streams, kGenThreads, smem, st>>>(p);
+  return cudaGetLastError();
+}
+template <int ALGO>
+static cudaError_t launch_sel_algo(const KernelParams& p, cudaStream_t st) {
+  switch (p.N) {
+    case 512: return launch_sel_n<ALGO, 512>(p, st);
+    case 1024: return launch_sel_n<ALGO, 1024>(p, st);
+    case 2048: return launch_sel_n<ALGO, 2048>(p, st);
+    case 4096: return launch_sel_n<ALGO, 4096>(p, st);
+  }
+  return cudaErrorNotSupported;
+}
+cudaError_t launch_frames_kernel_sel(int algo, const KernelParams& p, cudaStream_t st) {
+  if (p.M > kSelMaxM || p.C > kMaxC) return cudaErrorNotSupported;
+  switch (algo) {
+    case ALGO_MVDR: return launch_sel_algo<ALGO_MVDR>(p, st);
+    case ALGO_LCMV: return launch_sel_algo<ALGO_LCMV>(p, st);
+    case ALGO_GSS: return launch_sel_algo<ALGO_GSS>(p, st);
+  }
+  return cudaErrorNotSupported;
 }
 
 template <int NN>

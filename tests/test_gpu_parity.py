@@ -68,7 +68,7 @@ def test_das_hop_at_a_time_callback_matches_batch():
 # ---------------------------------------------------------------------------------------------
 # magnitude-gated nodes: mvdr / lcmv / gss (device-resident path, selection flags captured)
 # ---------------------------------------------------------------------------------------------
-def run_device(cfg, x, events=(), capture=True):
+def run_device(cfg, x, events=(), capture=True, H=H):
     import torch
     B, M, L = x.shape
     T = L // H
@@ -233,9 +233,34 @@ def test_other_frame_sizes_match_oracle(algo, mics, hop, kw):
     assert err <= REL_L2_TOL
 
 
+@pytest.mark.parametrize("algo,mics,hop,interf,events", [
+    ("mvdr", "circ8", 1024, (), ()), ("mvdr", "aira3", 256, (), ()), ("mvdr", "circ12", 512, (), ()), ("mvdr", "circ16", 512, (), ()),
+    ("lcmv", "circ8", 256, (80.0, -60.0, 150.0), ((15, "theta", 20.0), (25, "interf", 2, -55.0), (35, "interf", 4, 120.0), (45, "interf", 1, 119.5))),
+    ("lcmv", "circ12", 512, (80.0, -60.0), ()), ("gss", "circ8", 1024, (80.0, -60.0, 150.0), ((20, "theta", 20.0), (30, "interf", 4, 120.0))),
+    ("gss", "aira3", 2048, (), ())])
+def test_gated_nodes_other_shapes_match_oracle(algo, mics, hop, interf, events):
+    """mvdr / lcmv / gss outside the 1024-point, <= 8 microphone fast path: 512- to 4096-point frames and up to 16
+    microphones (north_star: solves for M <= 16) run the general gated kernel; same gates as the fast path."""
+    cfg = bf.make_config(algo, mics=mics, hop=hop, initial_angle=10.0, interferers=interf)
+    n_hops = 61
+    x = np.stack([synth_stream(bf.GEOMETRIES[mics], n_hops * hop, seed=500 + b) for b in range(2)])
+    ref, sel, _ = oracle_with_flags(cfg, x, events=events)
+    got, flags, b = run_device(cfg, x, events=events, H=hop)
+    assert sel.sum() > 500, "the test signal must exercise the gate"
+    assert np.array_equal(flags & 1, sel), "selected-bin set must be bit-exact"
+    o = Oracle(cfg)
+    o.process(x[0], events=events)
+    assert b.interferences == o.interferences
+    err = finite_rel_l2(got, ref)
+    print(algo, mics, "hop", hop, "rel_l2", err, "selected fraction", sel.mean())
+    assert err <= REL_L2_TOL
+
+
 def test_unsupported_shapes_fail_loudly():
     with pytest.raises(bf.BeamformError):
-        bf.Beamformer(bf.make_config("mvdr", mics="circ8", hop=2048), 1)      # mvdr is built for 1024-point frames
+        bf.Beamformer(bf.make_config("mvdr", mics="circ8", hop=2048), 1)      # 8 x 4096-point spectra exceed shared memory
+    with pytest.raises(bf.BeamformError):
+        bf.Beamformer(bf.make_config("mvdr", mics="grid64"), 1)               # solves are built for <= 16 microphones
     with pytest.raises(bf.BeamformError):
         bf.Beamformer(bf.make_config("das", mics="circ8", hop=2048), 1)       # 8 x 4096-point spectra exceed shared memory
     with pytest.raises(bf.BeamformError):
