@@ -19,6 +19,7 @@
 namespace bf {
 
 constexpr int kSrpL = 514;   // logical bins of a 1024-point frame
+constexpr int kSrpTilePitch = 1026;   // float2 per warp tile in srp_spectra_kernel
 
 __device__ __forceinline__ void srp_fft1024_fwd(float2 (&v)[32], float2* tile, const float2* __restrict__ tw, int lane) {
 #pragma unroll 1
@@ -62,37 +63,50 @@ __global__ void __launch_bounds__(256, 1) srp_spectra_kernel(const KernelParams 
   double sd, cd;
   sincospi((double)lane / 1024.0, &sd, &cd);
   const float s_l = (float)(0.5 * sd), c_l = (float)(0.5 * cd);
-  float2* tile = tiles + (size_t)warp * 1024;
+  // tile pitch 1026 float2: 16-byte aligned, and the eight tiles of a round sit two 8-byte banks apart, so the
+  // transposing read below (eight lanes = eight microphones at the same bin) is conflict-free
+  float2* tile = tiles + (size_t)warp * kSrpTilePitch;
   const size_t F = (size_t)p.n_streams * n_hops;
   const size_t f0 = (size_t)s * n_hops + t;
-  for (int ch = warp; ch < M; ch += 8) {
-    const float* base = p.in + (size_t)s * p.in_stream_stride + (size_t)ch * p.in_mic_stride;
-    const float* ha = (t - 1 < 0) ? p.prev_hop + ((size_t)s * M + ch) * H : base + (size_t)(t - 1) * H;
-    const float* hb = base + (size_t)t * H;
-    const float* hc = two ? base + (size_t)(t + 1) * H : hb;
-    float2 v[32];
-    static_for<0, 16>([&](auto r) {
-      const float a = __ldg(ha + 32 * r + lane), bb = __ldg(hb + 32 * r + lane);
-      const float c = two ? __ldg(hc + 32 * r + lane) : 0.0f;
-      const float w0 = win1024<r>(s_l, c_l);
-      const float w1 = win1024<r + 16>(s_l, c_l);
-      v[brev5(r)] = make_float2(a * w0, bb * w0);
-      v[brev5(r + 16)] = make_float2(bb * w1, c * w1);
-    });
-    srp_fft1024_fwd(v, tile, tw, lane);
+  for (int r0 = 0; r0 < M; r0 += 8) {
+    const int ch = r0 + warp;
+    if (ch < M) {
+      const float* base = p.in + (size_t)s * p.in_stream_stride + (size_t)ch * p.in_mic_stride;
+      const float* ha = (t - 1 < 0) ? p.prev_hop + ((size_t)s * M + ch) * H : base + (size_t)(t - 1) * H;
+      const float* hb = base + (size_t)t * H;
+      const float* hc = two ? base + (size_t)(t + 1) * H : hb;
+      float2 v[32];
+      static_for<0, 16>([&](auto r) {
+        const float a = __ldg(ha + 32 * r + lane), bb = __ldg(hb + 32 * r + lane);
+        const float c = two ? __ldg(hc + 32 * r + lane) : 0.0f;
+        const float w0 = win1024<r>(s_l, c_l);
+        const float w1 = win1024<r + 16>(s_l, c_l);
+        v[brev5(r)] = make_float2(a * w0, bb * w0);
+        v[brev5(r + 16)] = make_float2(bb * w1, c * w1);
+      });
+      srp_fft1024_fwd(v, tile, tw, lane);
 #pragma unroll
-    for (int k2 = 0; k2 < 32; k2++) tile[k2 * 32 + lane] = v[k2];
-    __syncwarp();
-    for (int l = lane; l < kSrpL; l += 32) {
-      const int j = (l == kSrpL - 1) ? 511 : l;
-      const float2 a = tile[j], b = tile[(1024 - j) & 1023];
-      float2 x0 = make_float2(a.x + b.x, a.y - b.y);
-      float2 x1 = make_float2(a.y + b.y, b.x - a.x);
-      if (l == kSrpL - 1) { x0.y = -x0.y; x1.y = -x1.y; }   // pseudo-bin: conj of bin N/2-1 (SURVEY B-4)
-      xs[((size_t)l * F + f0) * M + ch] = x0;
-      if (two) xs[((size_t)l * F + f0 + 1) * M + ch] = x1;
+      for (int k2 = 0; k2 < 32; k2++) tile[k2 * 32 + lane] = v[k2];
     }
-    __syncwarp();
+    __syncthreads();
+    // The eight spectra of the round leave together: lanes 8q..8q+7 carry the eight microphones of one bin, so every
+    // (bin, frame) gets one 64-byte run of XS[l][f][r0..r0+7] (full sectors) instead of eight scattered 8-byte stores.
+    {
+      const int m = tid & 7;
+      if (r0 + m < M) {
+        const float2* zt = tiles + (size_t)m * kSrpTilePitch;
+        for (int l = tid >> 3; l < kSrpL; l += 32) {
+          const int j = (l == kSrpL - 1) ? 511 : l;
+          const float2 a = zt[j], b = zt[(1024 - j) & 1023];
+          float2 x0 = make_float2(a.x + b.x, a.y - b.y);
+          float2 x1 = make_float2(a.y + b.y, b.x - a.x);
+          if (l == kSrpL - 1) { x0.y = -x0.y; x1.y = -x1.y; }   // pseudo-bin: conj of bin N/2-1 (SURVEY B-4)
+          xs[((size_t)l * F + f0) * M + r0 + m] = x0;
+          if (two) xs[((size_t)l * F + f0 + 1) * M + r0 + m] = x1;
+        }
+      }
+    }
+    __syncthreads();
   }
 }
 
@@ -184,7 +198,7 @@ cudaError_t launch_srp_power_tc(const float2* xs, const double* tau, const doubl
 
 cudaError_t launch_srp(const KernelParams& p, float2* xs, const double* tau, const double* freqs_l, float* maps, int D, int n_hops,
                        cudaStream_t st) {
-  const size_t smem1 = sizeof(float2) * (1024 + 8 * 1024);
+  const size_t smem1 = sizeof(float2) * (1024 + 8 * kSrpTilePitch);
   cudaError_t e = cudaFuncSetAttribute(srp_spectra_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1);
   if (e != cudaSuccess) return e;
   dim3 g1((n_hops + 1) / 2, p.n_streams);

@@ -1,0 +1,38 @@
+#!/usr/bin/env python
+"""profiles/traffic_<workload>.json from an `ncu --csv --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum`
+log of one bench.py run: DRAM bytes per launch of the dominant (longest) kernel, averaged over its launches.
+usage: python tools/ncu_traffic.py <ncu.csv> <workload> [out_dir]"""
+import csv
+import json
+import os
+import sys
+from collections import defaultdict
+
+path, wl = sys.argv[1], sys.argv[2]
+out_dir = sys.argv[3] if len(sys.argv) > 3 else os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "profiles")
+rows = [r for r in csv.reader(open(path, errors="replace")) if len(r) > 10]
+hdr = rows[0]
+iK, iM, iU, iV = hdr.index("Kernel Name"), hdr.index("Metric Name"), hdr.index("Metric Unit"), hdr.index("Metric Value")
+iID = hdr.index("ID")
+scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "ns": 1e-9, "us": 1e-6, "ms": 1e-3, "s": 1.0, "usecond": 1e-6, "msecond": 1e-3, "nsecond": 1e-9, "second": 1.0}
+per = defaultdict(dict)
+for r in rows[1:]:
+    if not any(k in r[iK] for k in ("bf::", "das_pairs_kernel", "sel_pairs_kernel", "frames_kernel", "srp_", "save_prev_hop", "gss_reset", "zero_hops")):
+        continue
+    per[(r[iID], r[iK])][r[iM]] = float(r[iV].replace(",", "")) * scale.get(r[iU], 1.0)
+agg = defaultdict(lambda: [0, 0.0, 0.0, 0.0])
+for (_, k), m in per.items():
+    a = agg[k]
+    a[0] += 1
+    a[1] += m.get("gpu__time_duration.sum", 0.0)
+    a[2] += m.get("dram__bytes_read.sum", 0.0)
+    a[3] += m.get("dram__bytes_write.sum", 0.0)
+if not agg:
+    sys.exit("no bf:: kernels in " + path)
+k, a = max(agg.items(), key=lambda kv: kv[1][1])
+out = {"workload": wl, "kernel": k, "launches": a[0], "dram_bytes_read_per_launch": a[2] / a[0], "dram_bytes_write_per_launch": a[3] / a[0],
+       "dram_bytes_per_launch": (a[2] + a[3]) / a[0], "ncu_time_ms_per_launch": 1e3 * a[1] / a[0],
+       "share_of_bf_kernel_time": a[1] / sum(v[1] for v in agg.values()),
+       "source": "ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none (bench shape)"}
+json.dump(out, open(os.path.join(out_dir, "traffic_%s.json" % wl), "w"), indent=1)
+print(json.dumps(out))
