@@ -93,7 +93,7 @@ __device__ __forceinline__ void split_store2(unsigned char* hi, unsigned char* l
   *reinterpret_cast<__nv_bfloat162*>(lo + off) = l2;
 }
 
-// grid = (ceil(F/128), ceil(D/120)); block = 256; maps[f][d]
+// grid = (ceil(D/120), ceil(F/128)); block = 256; maps[f][d]
 __global__ void __launch_bounds__(256, 1) srp_power_tc_kernel(const float2* __restrict__ xs, const double* __restrict__ tau,
                                                                const double* __restrict__ freqs_l, float* __restrict__ maps, int D, int M,
                                                                long long F) {
@@ -105,8 +105,9 @@ __global__ void __launch_bounds__(256, 1) srp_power_tc_kernel(const float2* __re
   uint64_t* bar = reinterpret_cast<uint64_t*>(b_lo + kTileB);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const long long fbase = (long long)blockIdx.x * kTcM;
-  const int dbase = blockIdx.y * kTcD;
+  // direction tile fastest: the CTAs that sweep the same 128 frames run together and share the spectra through L2
+  const long long fbase = (long long)blockIdx.y * kTcM;
+  const int dbase = blockIdx.x * kTcD;
   const float invM = 1.0f / (float)M;
 
   if (tid == 0) mbar_init(bar, 1);
@@ -185,10 +186,20 @@ __global__ void __launch_bounds__(256, 1) srp_power_tc_kernel(const float2* __re
         ar[u] = on ? cs * invM : 0.f;
         ai[u] = on ? sn * invM : 0.f;
       }
-      split_store2(b_hi, b_lo, tile_off(d, i, kLboB), ar[0], ar[1]);                // Re row: [ Ar | -Ai ]
-      split_store2(b_hi, b_lo, tile_off(d, 64 + i, kLboB), -ai[0], -ai[1]);
-      split_store2(b_hi, b_lo, tile_off(kTcD + d, i, kLboB), ai[0], ai[1]);         // Im row: [ Ai |  Ar ]
-      split_store2(b_hi, b_lo, tile_off(kTcD + d, 64 + i, kLboB), ar[0], ar[1]);
+      // every value sits in two rows (Re row [ Ar | -Ai ], Im row [ Ai | Ar ]): split into bf16 hi/lo once, negate by sign bit
+      __nv_bfloat162 rh, rl, ih, il;
+      rh.x = __float2bfloat16_rn(ar[0]); rh.y = __float2bfloat16_rn(ar[1]);
+      rl.x = __float2bfloat16_rn(ar[0] - __bfloat162float(rh.x)); rl.y = __float2bfloat16_rn(ar[1] - __bfloat162float(rh.y));
+      ih.x = __float2bfloat16_rn(ai[0]); ih.y = __float2bfloat16_rn(ai[1]);
+      il.x = __float2bfloat16_rn(ai[0] - __bfloat162float(ih.x)); il.y = __float2bfloat16_rn(ai[1] - __bfloat162float(ih.y));
+      const uint32_t rhu = *reinterpret_cast<uint32_t*>(&rh), rlu = *reinterpret_cast<uint32_t*>(&rl);
+      const uint32_t ihu = *reinterpret_cast<uint32_t*>(&ih), ilu = *reinterpret_cast<uint32_t*>(&il);
+      const uint32_t o_re = tile_off(d, i, kLboB), o_im = tile_off(kTcD + d, i, kLboB);
+      const uint32_t kh = (uint32_t)(8 * kLboB);   // + 64 along K: eight K-cores further
+      *reinterpret_cast<uint32_t*>(b_hi + o_re) = rhu;                 *reinterpret_cast<uint32_t*>(b_lo + o_re) = rlu;
+      *reinterpret_cast<uint32_t*>(b_hi + o_re + kh) = ihu ^ 0x80008000u; *reinterpret_cast<uint32_t*>(b_lo + o_re + kh) = ilu ^ 0x80008000u;
+      *reinterpret_cast<uint32_t*>(b_hi + o_im) = ihu;                 *reinterpret_cast<uint32_t*>(b_lo + o_im) = ilu;
+      *reinterpret_cast<uint32_t*>(b_hi + o_im + kh) = rhu;            *reinterpret_cast<uint32_t*>(b_lo + o_im + kh) = rlu;
     }
     fence_proxy_async();   // generic-proxy stores -> visible to the tensor core's async-proxy reads
     __syncthreads();
@@ -240,7 +251,7 @@ cudaError_t launch_srp_power_tc(const float2* xs, const double* tau, const doubl
   const size_t smem = 2 * (size_t)kTileA + 2 * (size_t)kTileB + 64;
   cudaError_t e = cudaFuncSetAttribute(srp_power_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  dim3 grid((unsigned)((F + kTcM - 1) / kTcM), (unsigned)((D + kTcD - 1) / kTcD));
+  dim3 grid((unsigned)((D + kTcD - 1) / kTcD), (unsigned)((F + kTcM - 1) / kTcM));
   srp_power_tc_kernel<<<grid, 256, smem, st>>>(xs, tau, freqs_l, maps, D, M, F);
   return cudaGetLastError();
 }
