@@ -239,6 +239,11 @@ def run_srp(args, wl, bf, rank, local_rank, world, cores):
         flops = 8.0 * D * M * 513 * B * T          # 8*D*M*(N/2+1) per frame
         ms_per_launch = elapsed_ms / args.steps
         achieved = flops / (ms_per_launch * 1e-3) / 1e12
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic_c5.json"))).get("dram_bytes_per_launch")
+        except Exception:
+            pass
         cpu = None
         if not args.no_cpu and world == 1:
             from beamform_b200.synth import synth_batch
@@ -259,7 +264,8 @@ def run_srp(args, wl, bf, rank, local_rank, world, cores):
                        "streams_per_gpu": B, "hops_per_step": T, "audio_s_per_step_per_gpu": B * L / SR,
                        "l2_policy": "spectra workspace (%d MB) larger than L2, no flush" % (514 * B * T * M * 8 // 2 ** 20),
                        "collective": "all_gather of maps (NCCL)" if world > 1 else "none"},
-            "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+            "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
+                         "traffic_note": "DRAM bytes per launch of srp_power_tc_kernel, the dominant kernel (ncu); the step also launches srp_spectra_kernel",
                          "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (of measured)" if peaks else "fallback 1400",
                          "kernel": "srp_power_tc_kernel (tcgen05 BF16x3) + srp_spectra_kernel", "kernel_ms_per_launch": ms_per_launch,
                          "algorithmic_flops_per_launch": flops,
