@@ -15,7 +15,7 @@ import numpy as np
 
 from . import build as _build
 
-ALGOS = {"das": 0, "mvdr": 1, "lcmv": 2, "gss": 3, "phase": 4, "phasempf": 5}
+ALGOS = {"das": 0, "mvdr": 1, "lcmv": 2, "gss": 3, "phase": 4, "phasempf": 5, "mcra": 6, "ref": 7}
 MAX_MICS = 64
 MAX_INTERF = 16
 
@@ -53,6 +53,8 @@ LAUNCH_PARAMS = {
     "phasempf": dict(min_phase=30.0, min_mag=0.05, smooth_size=3, MCRA_alphaS=0.95, MCRA_alphaD=0.95, MCRA_alphaD2=0.98,
                      MCRA_delta=0.001, MCRA_L=50, MPF_alphaS=0.7, MPF_eta=0.3, MPF_rev_gamma=0.9, MPF_rev_delta=1.0,
                      out_amp=2.5, noise_floor=0.001, out_only_noise=False, out_only_mcra=False),
+    "mcra": dict(alphaS=0.95, alphaD=0.95, alphaD2=0.98, delta=0.001, L=300, out_amp=3.5, out_only_noise=False),   # launch/mcra.launch
+    "ref": {},
 }
 
 # beamform_config.yaml geometries (lines 15-17, 38-39) and the synthetic ones SURVEY.md §8d names

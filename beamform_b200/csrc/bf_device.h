@@ -7,7 +7,7 @@
 
 namespace bf {
 
-enum { ALGO_DAS = 0, ALGO_MVDR = 1, ALGO_LCMV = 2, ALGO_GSS = 3, ALGO_PHASE = 4, ALGO_PHASEMPF = 5 };
+enum { ALGO_DAS = 0, ALGO_MVDR = 1, ALGO_LCMV = 2, ALGO_GSS = 3, ALGO_PHASE = 4, ALGO_PHASEMPF = 5, ALGO_MCRA = 6, ALGO_REF = 7 };
 
 // "Logical bins": the reference loops over all N FFT bins (das.cpp:60); inputs are real so bin N-j is
 // the conjugate of bin j and every per-bin rule is conjugate-equivariant EXCEPT at the pair

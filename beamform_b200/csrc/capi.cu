@@ -34,6 +34,8 @@ cudaError_t launch_frames_kernel_n(int algo, const KernelParams& p, cudaStream_t
 size_t frames_kernel_n_smem(int N, int M, int algo);
 cudaError_t launch_frames_kernel_sel(int algo, const KernelParams& p, cudaStream_t st);
 size_t frames_kernel_sel_smem(int N, int M);
+cudaError_t launch_frames_kernel_mcra(const KernelParams& p, cudaStream_t st);
+cudaError_t launch_ref_kernel(const KernelParams& p, cudaStream_t st);
 cudaError_t launch_srp(const KernelParams& p, float2* xs, const double* tau, const double* freqs_l, float* maps, int D, int n_hops,
                        cudaStream_t st);
 }   // namespace bf
@@ -131,7 +133,7 @@ struct bf_handle {
 // configuration
 // ------------------------------------------------------------------------------------------------
 extern "C" int bf_config_init(bf_config* c, int algo) {
-  if (!c || algo < 0 || algo > 5) return fail(BF_ERR_INVALID, "bf_config_init: bad arguments");
+  if (!c || algo < 0 || algo > 7) return fail(BF_ERR_INVALID, "bf_config_init: bad arguments");
   memset(c, 0, sizeof(*c));
   c->algo = algo;
   c->sample_rate = 48000;   // rosjack_config.yaml:9 (JACK decides at run time)
@@ -142,7 +144,7 @@ extern "C" int bf_config_init(bf_config* c, int algo) {
   c->freq_mag_threshold = 1.5;
   c->freq_max = 4000;
   c->freq_min = 400;
-  c->out_amp = (algo == BF_ALGO_PHASEMPF) ? 2.0 : 4.5;   // phasempf.cpp:451
+  c->out_amp = (algo == BF_ALGO_PHASEMPF || algo == BF_ALGO_MCRA) ? 2.0 : 4.5;   // phasempf.cpp:451, mcra.cpp:215
   c->interf_angle_threshold = 5.0;
   c->mu = 0.01;      // gss.cpp fall-back
   c->lambda = 0.0;
@@ -157,7 +159,8 @@ extern "C" int bf_config_init(bf_config* c, int algo) {
   c->MCRA_L = 0;     // "MCRA_L = 0.01" assigned to an int (phasempf.cpp:416)
   c->MPF_alphaS = 0.3; c->MPF_eta = 0.3; c->MPF_rev_gamma = 0.3; c->MPF_rev_delta = 1.0;
   c->noise_floor = 0.001;
-  c->out_only_noise = 0; c->out_only_mcra = 0;
+  c->out_only_noise = (algo == BF_ALGO_MCRA) ? 1 : 0;   // mcra.cpp:222: the fall-back is `true`
+  c->out_only_mcra = 0;
   c->dropped_hops_on_restructure = 0;
   c->device = 0;
   return BF_OK;
@@ -182,6 +185,12 @@ extern "C" int bf_config_set(bf_config* c, const char* key_c, const char* val_c)
   if (key == "past_windows") { c->past_windows = (uint32_t)(int)v; return BF_OK; }   // mvdr.cpp:152 (int) cast
   if (key == "smooth_size") { c->smooth_size = (int)v < 1 ? 20 : (int)v; return BF_OK; }   // phasempf.cpp:377-381
   if (key == "MCRA_L") { c->MCRA_L = (int)v; return BF_OK; }
+  // the stand-alone mcra node names the same quantities without the prefix (mcra.cpp:181-224)
+  if (key == "alphaS") { c->MCRA_alphaS = v; return BF_OK; }
+  if (key == "alphaD") { c->MCRA_alphaD = v; return BF_OK; }
+  if (key == "alphaD2") { c->MCRA_alphaD2 = v; return BF_OK; }
+  if (key == "delta") { c->MCRA_delta = v; return BF_OK; }
+  if (key == "L") { c->MCRA_L = (int)v; return BF_OK; }
   if (key == "hop" || key == "period") { c->hop = (uint32_t)v; return BF_OK; }
   if (key == "out_only_noise") { c->out_only_noise = parse_bool(val); return BF_OK; }
   if (key == "out_only_mcra") { c->out_only_mcra = parse_bool(val); return BF_OK; }
@@ -372,7 +381,7 @@ extern "C" int bf_create(bf_handle** out, const bf_config* cfg, uint32_t n_strea
     if (!sel && cfg->hop != 512 && bf::frames_kernel_n_smem(2 * (int)cfg->hop, cfg->n_mics, cfg->algo) > 232448)
       return fail(BF_ERR_INVALID, "bf_create: too many microphones for this frame size (spectra must fit 227 KB of shared memory)");
   }
-  if (cfg->algo < 0 || cfg->algo > 5) return fail(BF_ERR_INVALID, "bf_create: unknown algo");
+  if (cfg->algo < 0 || cfg->algo > 7) return fail(BF_ERR_INVALID, "bf_create: unknown algo");
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1 || cfg->device >= ndev)
     return fail(BF_ERR_NO_DEVICE, "bf_create: no CUDA device (beamform_b200 has no CPU path)");
@@ -430,7 +439,7 @@ extern "C" int bf_create(bf_handle** out, const bf_config* cfg, uint32_t n_strea
     }
     h->Lsel = (int)list.size();
     const bool sel_algo = cfg->algo == BF_ALGO_MVDR || cfg->algo == BF_ALGO_LCMV || cfg->algo == BF_ALGO_GSS;
-    const bool pha_algo = cfg->algo == BF_ALGO_PHASE || cfg->algo == BF_ALGO_PHASEMPF;
+    const bool pha_algo = cfg->algo == BF_ALGO_PHASE || cfg->algo == BF_ALGO_PHASEMPF || cfg->algo == BF_ALGO_MCRA || cfg->algo == BF_ALGO_REF;
     if (pha_algo) {
       if (cfg->algo == BF_ALGO_PHASEMPF && (cfg->smooth_size < 1 || cfg->smooth_size > 64)) {
         bf_destroy(h);
@@ -613,6 +622,7 @@ static int run_segment(bf_handle* h, const float* in, size_t ss, size_t ms, floa
   p.frame_index0 = (int)(h->frames_done & 0x7fffffff);
   p.prev_hop = h->d_prev_hop; p.tail = h->d_tail;
   p.steer = h->d_steer; p.das_ceff = h->d_das_ceff; p.inband = h->d_inband; p.C = h->C;
+  // (mcra applies out_amp to the magnitudes itself, like phasempf)
   const bool amp = h->cfg.algo == BF_ALGO_MVDR || h->cfg.algo == BF_ALGO_LCMV || h->cfg.algo == BF_ALGO_GSS;
   p.out_scale = (float)((amp ? h->cfg.out_amp : 1.0) / (double)h->N);
   if (h->d_capture) {
@@ -665,7 +675,9 @@ static int run_segment(bf_handle* h, const float* in, size_t ss, size_t ms, floa
   const bool gen_algo = h->cfg.algo == BF_ALGO_DAS || h->cfg.algo == BF_ALGO_PHASE || h->cfg.algo == BF_ALGO_PHASEMPF;
   static const bool force_sel_generic = getenv("BF_SEL_GENERIC") != nullptr;   // debug: cross-check the general gated kernel
   const bool sel_algo = h->cfg.algo == BF_ALGO_MVDR || h->cfg.algo == BF_ALGO_LCMV || h->cfg.algo == BF_ALGO_GSS;
-  if (sel_algo && (h->N != 1024 || force_sel_generic || (h->M > 8 && h->cfg.algo != BF_ALGO_GSS)))
+  if (h->cfg.algo == BF_ALGO_MCRA) CUDA_TRY(bf::launch_frames_kernel_mcra(p, st));
+  else if (h->cfg.algo == BF_ALGO_REF) CUDA_TRY(bf::launch_ref_kernel(p, st));
+  else if (sel_algo && (h->N != 1024 || force_sel_generic || (h->M > 8 && h->cfg.algo != BF_ALGO_GSS)))
     CUDA_TRY(bf::launch_frames_kernel_sel(h->cfg.algo, p, st));
   else if (h->N != 1024 || (force_generic && gen_algo)) CUDA_TRY(bf::launch_frames_kernel_n(h->cfg.algo, p, st));
   else if (h->cfg.algo == BF_ALGO_DAS && bf::das_pairs_supported(p)) CUDA_TRY(bf::launch_das_pairs(p, st, h->sm_count));
@@ -679,8 +691,8 @@ static int run_segment(bf_handle* h, const float* in, size_t ss, size_t ms, floa
   h->launches += 2;
   if (s0 + p.n_streams >= h->B) {   // the last stream chunk closes the segment
     h->frames_done += h1 - h0;
-    if (h->cfg.algo == BF_ALGO_PHASEMPF)
-      for (uint32_t t = h0; t < h1; t++) {   // phasempf.cpp:162-176: window counters advance once per frame
+    if (h->cfg.algo == BF_ALGO_PHASEMPF || h->cfg.algo == BF_ALGO_MCRA)
+      for (uint32_t t = h0; t < h1; t++) {   // phasempf.cpp:162-176, mcra.cpp:100-113: window counters advance once per frame
         if (h->mcra_cur_L > h->cfg.MCRA_L) { h->mcra_cur_L = 1; h->mcra_first = 0; } else h->mcra_cur_L++;
       }
   }

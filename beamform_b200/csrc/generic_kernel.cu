@@ -1236,6 +1236,198 @@ cudaError_t launch_frames_kernel_sel(int algo, const KernelParams& p, cudaStream
   return cudaErrorNotSupported;
 }
 
+// =====================================================================================================================
+// Stand-alone MCRA noise-reduction node: mcra.cpp:62-155 on the FIRST microphone only.
+//   |X|^2 -> 3-tap smoothing over neighbouring bins (this node does read its neighbours, unlike phasempf's copy,
+//   SURVEY B-9) -> recursive averaging -> minima tracking over windows of L frames -> noise estimate lambda ->
+//   Y = max(0, |X| - sqrt(lambda)) * out_amp * e^{i arg X}  (or the noise estimate itself); Y[0] is never written
+//   (mcra.cpp:127 has the one-past-the-end write of SURVEY B-5).
+// The recursion is conjugate-symmetric (|X[N-j]| = |X[j]|, symmetric window, symmetric index clipping at 1 and N-1),
+// so the half spectrum carries it; no frequency table is involved, hence no pseudo-bin.
+// State [B][7][L] (layout shared with phasempf; slots 0-3: S_prev, S_tmp, S_min, lambda).
+// =====================================================================================================================
+template <int NN>
+struct McraScratch {
+  float psq[2][NN / 2 + 2];   // |X_f[l]|^2, l = 0..N/2
+  float tail[NN / 2];
+};
+
+template <int NN>
+__global__ void __launch_bounds__(kGenThreads, 1) frames_kernel_mcra(const __grid_constant__ KernelParams p) {
+  constexpr int H = NN / 2, L = NN / 2 + 2;
+  unsigned char* smem_raw = gen_smem_raw;
+  float2* zbuf = reinterpret_cast<float2*>(smem_raw);   // [NN] packed spectrum of microphone 0
+  float2* gbuf = zbuf + NN;                              // [NN]
+  McraScratch<NN>& sc = *reinterpret_cast<McraScratch<NN>*>(gbuf + NN);
+  const unsigned g_off = (unsigned)(NN * sizeof(float2));
+  const int tid = threadIdx.x;
+  const int s = blockIdx.x + p.stream_begin;
+  const float2* tw = p.twid_f;
+  const float* win = p.win_f;
+  int cur_L = p.mcra_cur_L0, first_L = p.mcra_first0;
+  float* stg = p.mpf_state + (size_t)s * 7 * L;
+
+  for (int i = tid; i < H; i += kGenThreads) sc.tail[i] = p.tail[(size_t)s * H + i];
+  __syncthreads();
+  const int nh = p.hop_end - p.hop_begin;
+  const int npairs = (nh + 1) >> 1;
+  for (int ip = 0; ip < npairs; ip++) {
+    const int t = p.hop_begin + 2 * ip;
+    const bool two = t + 1 < p.hop_end;
+    const int nf = two ? 2 : 1;
+    {   // window + pack (util.h:217-242), first channel only
+      const float* base = p.in + (size_t)s * p.in_stream_stride;
+      const float* ha = (t - 1 < 0) ? p.prev_hop + (size_t)s * p.M * H : base + (size_t)(t - 1) * H;
+      const float* hb = base + (size_t)t * H;
+      const float* hc = two ? base + (size_t)(t + 1) * H : hb;
+      for (int n = tid; n < H; n += kGenThreads) {
+        const float a = __ldg(ha + n), b = __ldg(hb + n), c = two ? __ldg(hc + n) : 0.f;
+        const float w0 = 0.5f * __ldg(win + n), w1 = 0.5f * __ldg(win + n + H);
+        zbuf[swz(n)] = make_float2(a * w0, (two ? b : 0.f) * w0);
+        zbuf[swz(n + H)] = make_float2(b * w1, c * w1);
+      }
+    }
+    __syncthreads();
+    block_fft_fn<NN, -1, float2>(0u, 1, tw, tid);
+    for (int l = tid; l <= H; l += kGenThreads) {   // in_fft_square (mcra.cpp:73-76)
+      const float2 a = zbuf[swz(l)], b = zbuf[swz((NN - l) & (NN - 1))];
+      const float2 x0 = make_float2(a.x + b.x, a.y - b.y), x1 = make_float2(a.y + b.y, b.x - a.x);
+      sc.psq[0][l] = fmaf(x0.x, x0.x, x0.y * x0.y);
+      sc.psq[1][l] = fmaf(x1.x, x1.x, x1.y * x1.y);
+    }
+    __syncthreads();
+    // window bookkeeping of the two frames (mcra.cpp:100-113), global per frame
+    bool reset_f[2] = {false, false};
+    float inv_cl_f[2] = {1.f, 1.f};
+    int fst_f[2] = {first_L, first_L};
+    for (int f = 0; f < nf; f++) {
+      const bool r = cur_L > p.mcra_L;
+      if (r) { cur_L = 1; first_L = 0; } else { cur_L++; }
+      reset_f[f] = r; inv_cl_f[f] = 1.0f / (float)cur_L; fst_f[f] = first_L;
+    }
+    for (int l = tid; l <= H; l += kGenThreads) {
+      const float2 a = zbuf[swz(l)], b = zbuf[swz((NN - l) & (NN - 1))];
+      const float2 xf[2] = {make_float2(a.x + b.x, a.y - b.y), make_float2(a.y + b.y, b.x - a.x)};
+      float S_prev = stg[0 * L + l], S_tmp = stg[1 * L + l], S_min = stg[2 * L + l], lam = stg[3 * L + l];
+      float2 yy[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+      for (int f = 0; f < nf; f++) {
+        const float* ps = sc.psq[f];
+        const float pq = ps[l];
+        float Sf;
+        if (l == 0) {
+          Sf = sqrtf(pq);   // "passing on the DC component": abs, not squared (mcra.cpp:81)
+        } else {
+          // neighbours j-1, j, j+1 clipped to [1, N-1]; bin N/2+1 is the mirror of N/2-1
+          const float lo = (l - 1 >= 1) ? ps[l - 1] : 0.f;
+          const float hi = (l + 1 <= H) ? ps[l + 1] : ps[H - 1];
+          Sf = 0.25f * lo + 0.5f * pq + 0.25f * hi;
+        }
+        const float S = p.mcra_alphaS * S_prev + (1.0f - p.mcra_alphaS) * Sf;
+        if (reset_f[f]) { S_min = fminf(S_tmp, S); S_tmp = S; }
+        else { S_min = fminf(S_min, S); S_tmp = fminf(S_tmp, S); }
+        if (fst_f[f] || S < S_min * p.mcra_delta || lam > pq) {
+          if (fst_f[f] && inv_cl_f[f] > p.mcra_alphaD) lam = inv_cl_f[f] * lam + (1.0f - inv_cl_f[f]) * pq;
+          else lam = p.mcra_alphaD2 * lam + (1.0f - p.mcra_alphaD) * pq;
+        }
+        S_prev = S;
+        if (l > 0) {
+          const float mag_x = sqrtf(pq);
+          float mag;
+          if (p.out_only_noise) {
+            mag = sqrtf(lam) * p.out_amp;
+          } else {
+            mag = (mag_x - sqrtf(lam)) * p.out_amp;
+            if (mag < 0.f) mag = 0.f;
+          }
+          const float r0 = rsqrtf(pq);
+          const float2 unit = pq > 0.f ? make_float2(xf[f].x * r0, xf[f].y * r0) : make_float2(1.f, 0.f);   // e^{i arg X}
+          yy[f] = make_float2(mag * unit.x, mag * unit.y);
+        }
+      }
+      stg[0 * L + l] = S_prev; stg[1 * L + l] = S_tmp; stg[2 * L + l] = S_min; stg[3 * L + l] = lam;
+      float2 y0 = yy[0], y1 = yy[1];
+      if (l == 0 || l == H) { y0.y = 0.f; y1.y = 0.f; }
+      gbuf[swz(l)] = make_float2(y0.x - y1.y, y0.y + y1.x);
+      if (l > 0 && l < H) gbuf[swz(NN - l)] = make_float2(y0.x + y1.y, y1.x - y0.y);
+    }
+    __syncthreads();
+    const float2* res = reinterpret_cast<const float2*>(smem_raw + block_fft_oop_fn<NN, 1, float2>(g_off, 0u, tw, tid));
+    float* o0 = p.out + (size_t)s * p.out_stream_stride + (size_t)t * H;
+    for (int n = tid; n < H; n += kGenThreads) {   // util.h:244-253, 301-302
+      const float w0 = __ldg(win + n) * p.out_scale, w1 = __ldg(win + n + H) * p.out_scale;
+      const float2 a = res[swz(n)], b = res[swz(n + H)];
+      o0[n] = sc.tail[n] + a.x * w0;
+      if (two) {
+        o0[H + n] = b.x * w1 + a.y * w0;
+        sc.tail[n] = b.y * w1;
+      } else {
+        sc.tail[n] = b.x * w1;
+      }
+    }
+    __syncthreads();
+  }
+  for (int i = tid; i < H; i += kGenThreads) p.tail[(size_t)s * H + i] = sc.tail[i];
+}
+
+template <int NN>
+static cudaError_t launch_mcra_n(const KernelParams& p, cudaStream_t st) {
+  const size_t smem = sizeof(float2) * 2 * NN + sizeof(McraScratch<NN>) + 16;
+  cudaError_t e = cudaFuncSetAttribute(frames_kernel_mcra<NN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  frames_kernel_mcra<NN><<<p.n_streams, kGenThreads, smem, st>>>(p);
+  return cudaGetLastError();
+}
+cudaError_t launch_frames_kernel_mcra(const KernelParams& p, cudaStream_t st) {
+  switch (p.N) {
+    case 512: return launch_mcra_n<512>(p, st);
+    case 1024: return launch_mcra_n<1024>(p, st);
+    case 2048: return launch_mcra_n<2048>(p, st);
+    case 4096: return launch_mcra_n<4096>(p, st);
+  }
+  return cudaErrorNotSupported;
+}
+
+// =====================================================================================================================
+// rosjack_ref: jack_ref.cpp:19-60 + util.h:347-372.  The first microphone, windowed twice
+// (analysis in overlap_and_add_prepare_input, then jack_ref.cpp:28) and overlap-added: both terms of an output sample
+// come from the same input sample of the PREVIOUS hop,
+//     out[t][j] = fl32(fl32(x w[j+H]) w[j+H]) + fl32(fl32(x w[j]) w[j]),   x = hop_{t-1}[j], products in double,
+// i.e. the input delayed by one hop up to float rounding (w^2[j] + w^2[j+H] = 1).  Pure streaming: 8 bytes per sample.
+// =====================================================================================================================
+__global__ void __launch_bounds__(256) ref_kernel(const __grid_constant__ KernelParams p) {
+  const int H = p.H;
+  const int nh = p.hop_end - p.hop_begin;
+  const long long per_stream = (long long)nh * H;   // multiple of 4 (H is)
+  const long long total4 = (long long)p.n_streams * per_stream / 4;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total4; i += (long long)gridDim.x * blockDim.x) {
+    const long long e = i * 4;
+    const int sl = (int)(e / per_stream);
+    const long long r = e - (long long)sl * per_stream;
+    const int t = p.hop_begin + (int)(r / H), j = (int)(r % H);
+    const int s = sl + p.stream_begin;
+    const float* src = (t - 1 < 0) ? p.prev_hop + (size_t)s * p.M * H + j
+                                   : p.in + (size_t)s * p.in_stream_stride + (size_t)(t - 1) * H + j;
+    const float4 x = *reinterpret_cast<const float4*>(src);
+    const double4 wa = make_double4(p.win_d[j], p.win_d[j + 1], p.win_d[j + 2], p.win_d[j + 3]);
+    const double4 wb = make_double4(p.win_d[j + H], p.win_d[j + H + 1], p.win_d[j + H + 2], p.win_d[j + H + 3]);
+    auto one = [](float xv, double w0, double w1) {
+      const float c = (float)((double)(float)((double)xv * w0) * w0);   // this frame, first half
+      const float q = (float)((double)(float)((double)xv * w1) * w1);   // previous frame, second half
+      return q + c;                                                       // util.h:362
+    };
+    float4 y;
+    y.x = one(x.x, wa.x, wb.x); y.y = one(x.y, wa.y, wb.y); y.z = one(x.z, wa.z, wb.z); y.w = one(x.w, wa.w, wb.w);
+    *reinterpret_cast<float4*>(p.out + (size_t)s * p.out_stream_stride + (size_t)t * H + j) = y;
+  }
+}
+cudaError_t launch_ref_kernel(const KernelParams& p, cudaStream_t st) {
+  // float4 path: 16-byte aligned bases and strides (the C ABI's staging buffers are; a caller's odd layout is rejected)
+  if ((reinterpret_cast<uintptr_t>(p.in) & 15) || (reinterpret_cast<uintptr_t>(p.out) & 15) || (p.in_stream_stride & 3) || (p.out_stream_stride & 3))
+    return cudaErrorMisalignedAddress;
+  ref_kernel<<<148 * 8, 256, 0, st>>>(p);
+  return cudaGetLastError();
+}
+
 template <int NN>
 static size_t gen_smem(int M, bool pha) { return (pha ? sizeof(double2) : sizeof(float2)) * (size_t)M * NN + sizeof(float2) * NN + sizeof(GenScratch<NN>) + 16; }
 

@@ -47,6 +47,11 @@ WORKLOADS = {
     # BASELINE.json configs[4]: steered-response sweep; streams are sharded across ranks and the maps are gathered (NCCL)
     "c5": dict(name="C5: 64-mic (8x8 grid, 4 cm) steered-response DAS sweep over 360 directions, 1024-pt", algo="das", mics="grid64",
                n_streams=100, hops_per_step=188, interferers=(), kernel="srp_power_tc_kernel", srp_dirs=360),
+    # SURVEY.md section 8f rank 2 (single-channel nodes: 2 x 4 algorithmic bytes per sample)
+    "mcra": dict(name="MCRA node (mcra.launch), first microphone of aira3, 1024-pt", algo="mcra", mics="aira3", n_streams=2368, hops_per_step=188,
+                 interferers=(), kernel="frames_kernel_mcra<1024>", alg_channels=1),
+    "ref": dict(name="rosjack_ref passthrough (window^2 overlap-add), first microphone of aira3", algo="ref", mics="aira3", n_streams=2368,
+                hops_per_step=188, interferers=(), kernel="ref_kernel", alg_channels=1),
     "ph": dict(name="Phase 3-mic (aira3) 1024-pt phase mask", algo="phase", mics="aira3", n_streams=1184, hops_per_step=188,
                interferers=(), kernel="frames_kernel_1024<phase>"),
 }
@@ -415,7 +420,7 @@ def main():
         except Exception:
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
-        alg_bytes_per_launch = (M + 1) * 4.0 * B * L
+        alg_bytes_per_launch = (wl.get("alg_channels", M) + 1) * 4.0 * B * L
         achieved = alg_bytes_per_launch / (kern_ms / max(1, kern_n) * 1e-3) / 1e9 if kern_n else None
         traffic = None
         try:

@@ -17,6 +17,11 @@ CASES = {
     "phasempf_binaural": dict(algo="phasempf", mics="binaural", hops=170, seed=111, synth=dict(gate_hz=1.3)),
     "phasempf_aira3_only_mcra": dict(algo="phasempf", mics="aira3", hops=120, seed=112, synth=dict(gate_hz=1.3), cfg=dict(initial_angle=15.0, out_only_mcra=True)),
     "phasempf_binaural_hop2048_c4": dict(algo="phasempf", mics="binaural", hops=60, seed=113, hop=2048, synth=dict(gate_hz=1.3)),
+    # the stand-alone MCRA node (launch/mcra.launch) and rosjack_ref
+    "mcra_aira3": dict(algo="mcra", mics="aira3", hops=170, seed=114, synth=dict(gate_hz=1.3), cfg=dict(L=50)),
+    "mcra_binaural_hop2048_only_noise": dict(algo="mcra", mics="binaural", hops=60, seed=115, hop=2048, synth=dict(gate_hz=1.3), cfg=dict(L=20, out_only_noise=True)),
+    "ref_aira3": dict(algo="ref", mics="aira3", hops=40, seed=116),
+    "ref_circ8_hop256": dict(algo="ref", mics="circ8", hops=48, seed=117, hop=256),
 }
 
 

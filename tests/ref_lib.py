@@ -19,13 +19,18 @@ NODE_KEYS = {
     "phase": ["min_phase", "mag_mult", "mag_threshold"],
     "phasempf": ["min_phase", "min_mag", "smooth_size", "MCRA_alphaS", "MCRA_alphaD", "MCRA_alphaD2", "MCRA_delta", "MCRA_L",
                  "MPF_alphaS", "MPF_eta", "MPF_rev_gamma", "MPF_rev_delta", "out_amp", "noise_floor", "out_only_noise", "out_only_mcra"],
+    "mcra": ["alphaS", "alphaD", "alphaD2", "delta", "L", "out_amp", "out_only_noise"],
+    "ref": [],
 }
-INT_KEYS = {"past_windows", "smooth_size", "MCRA_L"}
+# rosparam name -> config field where they differ (the mcra node drops the MCRA_ prefix, mcra.cpp:181-224)
+KEY_FIELD = {"alphaS": "MCRA_alphaS", "alphaD": "MCRA_alphaD", "alphaD2": "MCRA_alphaD2", "delta": "MCRA_delta", "L": "MCRA_L", "lambda": "lambda_"}
+BINARY = {"ref": "jack_ref_ref"}
+INT_KEYS = {"past_windows", "smooth_size", "MCRA_L", "L"}
 BOOL_KEYS = {"out_only_noise", "out_only_mcra"}
 
 
 def available(algo="das"):
-    return os.path.exists(os.path.join(REF_DIR, algo + "_ref"))
+    return os.path.exists(os.path.join(REF_DIR, BINARY.get(algo, algo + "_ref")))
 
 
 def build():
@@ -36,7 +41,7 @@ def build():
 def run_ref(algo, cfg, x, events=(), want_interf=False):
     """cfg: beamform_b200.BfConfig (or the oracle's BfoConfig) — every field the node reads is passed as a rosparam.
     x: [M][L] float32.  Returns out [L] float32 (and the final interference list)."""
-    x = np.ascontiguousarray(x, dtype=np.float32)
+    x = np.ascontiguousarray(x[:1] if algo == "ref" else x, dtype=np.float32)   # rosjack_ref opens one JACK input (jack_ref.cpp:65)
     M, L = x.shape
     with tempfile.TemporaryDirectory() as td:
         pf, inf, outf, evf, itf = (os.path.join(td, n) for n in ("params.txt", "in.f32", "out.f32", "events.txt", "interf.txt"))
@@ -47,7 +52,7 @@ def run_ref(algo, cfg, x, events=(), want_interf=False):
             for k in range(cfg.n_angle_interf):
                 f.write("angle_interf%d %r\n" % (k + 1, float(cfg.angle_interf[k])))
             for key in NODE_KEYS[algo]:
-                v = getattr(cfg, "lambda_" if key == "lambda" else key)
+                v = getattr(cfg, KEY_FIELD.get(key, key))
                 if key in BOOL_KEYS:
                     f.write("%s %s\n" % (key, "true" if v else "false"))
                 elif key in INT_KEYS:
@@ -64,7 +69,7 @@ def run_ref(algo, cfg, x, events=(), want_interf=False):
         env = dict(os.environ, BFREF_PARAMS=pf, BFREF_IN=inf, BFREF_OUT=outf, BFREF_EVENTS=evf, BFREF_INTERF_OUT=itf,
                    BFREF_HOP=str(int(cfg.hop)), BFREF_SR=str(int(cfg.sample_rate)))
         env.pop("BFREF_VERBOSE", None)
-        subprocess.run([os.path.join(REF_DIR, algo + "_ref")], env=env, check=True, stdout=subprocess.DEVNULL)
+        subprocess.run([os.path.join(REF_DIR, BINARY.get(algo, algo + "_ref"))], env=env, check=True, stdout=subprocess.DEVNULL)
         out = np.fromfile(outf, dtype=np.float32)
         interf = [float(s) for s in open(itf).read().split()] if os.path.exists(itf) else []
     return (out, interf) if want_interf else out

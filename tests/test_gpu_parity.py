@@ -256,6 +256,22 @@ def test_gated_nodes_other_shapes_match_oracle(algo, mics, hop, interf, events):
     assert err <= REL_L2_TOL
 
 
+@pytest.mark.parametrize("algo,mics,hop,kw", [("mcra", "aira3", 512, dict(L=50)), ("mcra", "binaural", 2048, dict(L=20)), ("mcra", "circ8", 256, dict(L=30, out_only_noise=True)),
+                                              ("mcra", "aira3", 1024, {}), ("ref", "aira3", 512, {}), ("ref", "binaural", 2048, {})])
+def test_mcra_and_ref_nodes_match_oracle(algo, mics, hop, kw):
+    """the stand-alone MCRA node (mcra.cpp) and rosjack_ref (jack_ref.cpp), state carried across calls."""
+    cfg = bf.make_config(algo, mics=mics, hop=hop, **kw)
+    n_hops = 131
+    x = np.stack([synth_stream(bf.GEOMETRIES[mics], n_hops * hop, seed=600 + b, gate_hz=1.3) for b in range(3)])
+    ref = oracle_batch(cfg, x)
+    b = bf.Beamformer(cfg, n_streams=3)
+    k = 20 * hop
+    got = np.concatenate([b.process(x[:, :, :k]), b.process(x[:, :, k:k + hop]), b.process(x[:, :, k + hop:])], axis=1)
+    err = rel_l2(got, ref)
+    print(algo, mics, "hop", hop, kw, "rel_l2", err)
+    assert err <= (0.0 if algo == "ref" else REL_L2_TOL)   # rosjack_ref is elementwise float arithmetic: bit-exact
+
+
 def test_unsupported_shapes_fail_loudly():
     with pytest.raises(bf.BeamformError):
         bf.Beamformer(bf.make_config("mvdr", mics="circ8", hop=2048), 1)      # 8 x 4096-point spectra exceed shared memory
