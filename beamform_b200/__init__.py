@@ -15,7 +15,7 @@ import numpy as np
 
 from . import build as _build
 
-ALGOS = {"das": 0, "mvdr": 1, "lcmv": 2, "gss": 3, "phase": 4, "phasempf": 5, "mcra": 6, "ref": 7}
+ALGOS = {"das": 0, "mvdr": 1, "lcmv": 2, "gss": 3, "phase": 4, "phasempf": 5, "mcra": 6, "ref": 7, "gsc": 8}
 MAX_MICS = 64
 MAX_INTERF = 16
 
@@ -36,6 +36,7 @@ class BfConfig(C.Structure):
         ("MPF_alphaS", C.c_double), ("MPF_eta", C.c_double), ("MPF_rev_gamma", C.c_double), ("MPF_rev_delta", C.c_double),
         ("noise_floor", C.c_double), ("out_only_noise", C.c_int32), ("out_only_mcra", C.c_int32),
         ("dropped_hops_on_restructure", C.c_int32), ("device", C.c_int32),
+        ("use_vad", C.c_int32), ("vad_threshold", C.c_double), ("mu0", C.c_double), ("mu_max", C.c_double), ("filter_size", C.c_int32),
     ]
 
 
@@ -55,6 +56,7 @@ LAUNCH_PARAMS = {
                      out_amp=2.5, noise_floor=0.001, out_only_noise=False, out_only_mcra=False),
     "mcra": dict(alphaS=0.95, alphaD=0.95, alphaD2=0.98, delta=0.001, L=300, out_amp=3.5, out_only_noise=False),   # launch/mcra.launch
     "ref": {},
+    "gsc": dict(use_vad=False, vad_threshold=0.1, mu0=0.0001, mu_max=0.1, filter_size=128),   # launch/gsc.launch (write_mu is a log file)
 }
 
 # beamform_config.yaml geometries (lines 15-17, 38-39) and the synthetic ones SURVEY.md §8d names

@@ -7,7 +7,7 @@
 
 namespace bf {
 
-enum { ALGO_DAS = 0, ALGO_MVDR = 1, ALGO_LCMV = 2, ALGO_GSS = 3, ALGO_PHASE = 4, ALGO_PHASEMPF = 5, ALGO_MCRA = 6, ALGO_REF = 7 };
+enum { ALGO_DAS = 0, ALGO_MVDR = 1, ALGO_LCMV = 2, ALGO_GSS = 3, ALGO_PHASE = 4, ALGO_PHASEMPF = 5, ALGO_MCRA = 6, ALGO_REF = 7, ALGO_GSC = 8 };
 
 // "Logical bins": the reference loops over all N FFT bins (das.cpp:60); inputs are real so bin N-j is
 // the conjugate of bin j and every per-bin rule is conjugate-equivariant EXCEPT at the pair
@@ -65,6 +65,14 @@ struct KernelParams {
   int out_only_noise, out_only_mcra;
   int smooth_size;
   float* smooth_hist;       // [B][smooth_size-1] last OLA samples before hop 0 of this call
+  // ---- gsc (gsc.cpp:93-197) ----
+  float* gsc_aligned;       // [B][M][hops*H] workspace: per-microphone aligned signals of this launch (do_overlap_bymic output)
+  long long gsc_aligned_stream_stride;   // floats; microphone stride = hops*H of this launch
+  float* gsc_tail;          // [B][M][H] per-microphone overlap-add tails (out_buff_mic, util.h:336-344)
+  float* gsc_state;         // [B][(2(M-1)+1)][F]: blocking-matrix delay lines, NLMS filters, last outputs (rings: see gsc_head)
+  int* gsc_head;            // [B] ring position of logical tap 0
+  int gsc_F, gsc_use_vad;   // filter_size, use_vad
+  double gsc_vad_threshold, gsc_mu0, gsc_mu_max;
 };
 
 }   // namespace bf

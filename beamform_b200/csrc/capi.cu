@@ -36,6 +36,8 @@ cudaError_t launch_frames_kernel_sel(int algo, const KernelParams& p, cudaStream
 size_t frames_kernel_sel_smem(int N, int M);
 cudaError_t launch_frames_kernel_mcra(const KernelParams& p, cudaStream_t st);
 cudaError_t launch_ref_kernel(const KernelParams& p, cudaStream_t st);
+cudaError_t launch_gsc(const KernelParams& p, cudaStream_t st);
+size_t gsc_align_smem(int N, int M);
 cudaError_t launch_srp(const KernelParams& p, float2* xs, const double* tau, const double* freqs_l, float* maps, int D, int n_hops,
                        cudaStream_t st);
 }   // namespace bf
@@ -84,6 +86,9 @@ struct bf_handle {
   int sm_count = 148;
   float2* d_steer = nullptr;
   float2* d_das_ceff = nullptr;
+  float *d_gsc_aligned = nullptr, *d_gsc_tail = nullptr, *d_gsc_state = nullptr;   // gsc: workspace, per-mic OLA tails, delay lines + filters
+  int* d_gsc_head = nullptr;
+  size_t gsc_aligned_cap = 0;
   uint8_t* d_inband = nullptr;
   uint8_t* d_capture = nullptr;
   size_t steer_cap = 0;
@@ -133,7 +138,7 @@ struct bf_handle {
 // configuration
 // ------------------------------------------------------------------------------------------------
 extern "C" int bf_config_init(bf_config* c, int algo) {
-  if (!c || algo < 0 || algo > 7) return fail(BF_ERR_INVALID, "bf_config_init: bad arguments");
+  if (!c || algo < 0 || algo > 8) return fail(BF_ERR_INVALID, "bf_config_init: bad arguments");
   memset(c, 0, sizeof(*c));
   c->algo = algo;
   c->sample_rate = 48000;   // rosjack_config.yaml:9 (JACK decides at run time)
@@ -163,6 +168,8 @@ extern "C" int bf_config_init(bf_config* c, int algo) {
   c->out_only_mcra = 0;
   c->dropped_hops_on_restructure = 0;
   c->device = 0;
+  // gsc.cpp:206-258
+  c->use_vad = 0; c->vad_threshold = 0.1; c->mu0 = 0.0005; c->mu_max = 0.01; c->filter_size = 128;
   return BF_OK;
 }
 
@@ -180,8 +187,10 @@ extern "C" int bf_config_set(bf_config* c, const char* key_c, const char* val_c)
   KEYD(freq_mag_threshold) KEYD(freq_max) KEYD(freq_min) KEYD(out_amp) KEYD(interf_angle_threshold) KEYD(mu) KEYD(lambda)
   KEYD(min_phase) KEYD(mag_mult) KEYD(mag_threshold) KEYD(min_mag) KEYD(MCRA_alphaS) KEYD(MCRA_alphaD) KEYD(MCRA_alphaD2)
   KEYD(MCRA_delta) KEYD(MPF_alphaS) KEYD(MPF_eta) KEYD(MPF_rev_gamma) KEYD(MPF_rev_delta) KEYD(noise_floor)
-  KEYD(initial_angle) KEYD(sample_rate)
+  KEYD(initial_angle) KEYD(sample_rate) KEYD(vad_threshold) KEYD(mu0) KEYD(mu_max)
 #undef KEYD
+  if (key == "use_vad") { c->use_vad = parse_bool(val); return BF_OK; }
+  if (key == "filter_size") { c->filter_size = (int)v; return BF_OK; }
   if (key == "past_windows") { c->past_windows = (uint32_t)(int)v; return BF_OK; }   // mvdr.cpp:152 (int) cast
   if (key == "smooth_size") { c->smooth_size = (int)v < 1 ? 20 : (int)v; return BF_OK; }   // phasempf.cpp:377-381
   if (key == "MCRA_L") { c->MCRA_L = (int)v; return BF_OK; }
@@ -328,6 +337,17 @@ static int upload_tables(bf_handle* h, cudaStream_t st) {
         steer[((size_t)l * h->C + k) * M + i] = make_float2((float)w.real(), (float)w.imag());
       }
   CUDA_TRY(cudaMemcpyAsync(h->d_steer, steer.data(), sizeof(float2) * nsteer, cudaMemcpyHostToDevice, st));
+  if (h->cfg.algo == BF_ALGO_GSC) {
+    // gsc.cpp:62-65: x_fft[j] *= conj(w_ij), no 1/M; Re() of the inverse keeps the Hermitian part (see the DAS table below)
+    std::vector<float2> ceff((size_t)M * N);
+    for (uint32_t i = 0; i < M; i++)
+      for (uint32_t j = 0; j < N; j++) {
+        cd a = std::conj(W(h, j, i, 0)), b = W(h, (N - j) % N, i, 0);
+        cd c = (a + b) / 2.0;
+        ceff[(size_t)i * N + j] = make_float2((float)c.real(), (float)c.imag());
+      }
+    CUDA_TRY(cudaMemcpyAsync(h->d_das_ceff, ceff.data(), sizeof(float2) * ceff.size(), cudaMemcpyHostToDevice, st));
+  }
   if (h->cfg.algo == BF_ALGO_DAS) {
     // Y[j] = (1/M) sum_i conj(w_ij) X_i[j] (das.cpp:60-63), out = Re(IFFT(Y)) (util.h:249).  Re() keeps the
     // Hermitian part Yh[j] = (Y[j] + conj(Y[N-j]))/2 = ceff_i[j] X_i[j] with
@@ -381,7 +401,13 @@ extern "C" int bf_create(bf_handle** out, const bf_config* cfg, uint32_t n_strea
     if (!sel && cfg->hop != 512 && bf::frames_kernel_n_smem(2 * (int)cfg->hop, cfg->n_mics, cfg->algo) > 232448)
       return fail(BF_ERR_INVALID, "bf_create: too many microphones for this frame size (spectra must fit 227 KB of shared memory)");
   }
-  if (cfg->algo < 0 || cfg->algo > 7) return fail(BF_ERR_INVALID, "bf_create: unknown algo");
+  if (cfg->algo < 0 || cfg->algo > 8) return fail(BF_ERR_INVALID, "bf_create: unknown algo");
+  if (cfg->algo == BF_ALGO_GSC) {
+    if (cfg->filter_size < 32 || cfg->filter_size > 256 || cfg->filter_size % 32) return fail(BF_ERR_INVALID, "bf_create: gsc filter_size must be a multiple of 32 in [32, 256]");
+    if (cfg->n_mics > 16) return fail(BF_ERR_INVALID, "bf_create: gsc supports at most 16 microphones");
+    if (bf::gsc_align_smem(2 * (int)cfg->hop, cfg->n_mics) > 232448)
+      return fail(BF_ERR_INVALID, "bf_create: too many microphones for this frame size (spectra must fit 227 KB of shared memory)");
+  }
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1 || cfg->device >= ndev)
     return fail(BF_ERR_NO_DEVICE, "bf_create: no CUDA device (beamform_b200 has no CPU path)");
@@ -494,6 +520,17 @@ extern "C" int bf_create(bf_handle** out, const bf_config* cfg, uint32_t n_strea
     cudaMemcpy(h->d_win_f, wf.data(), sizeof(float) * h->N, cudaMemcpyHostToDevice);
     cudaMemcpy(h->d_twid_f, tf.data(), sizeof(float2) * h->N, cudaMemcpyHostToDevice);
   }
+  if (cfg->algo == BF_ALGO_GSC) {
+    const size_t nt = (size_t)h->B * h->M * h->H, nst = (size_t)h->B * (2 * (h->M - 1) + 1) * cfg->filter_size;
+    if (cudaMalloc(&h->d_gsc_tail, sizeof(float) * nt) != cudaSuccess || cudaMalloc(&h->d_gsc_state, sizeof(float) * nst) != cudaSuccess ||
+        cudaMalloc(&h->d_gsc_head, sizeof(int) * h->B) != cudaSuccess) {
+      bf_destroy(h);
+      return fail(BF_ERR_ALLOC, "bf_create: device allocation failed (gsc state)");
+    }
+    cudaMemset(h->d_gsc_tail, 0, sizeof(float) * nt);      // util.h:341-342 calloc
+    cudaMemset(h->d_gsc_state, 0, sizeof(float) * nst);    // gsc.cpp:286-289 calloc
+    cudaMemset(h->d_gsc_head, 0, sizeof(int) * h->B);
+  }
   cudaMemset(h->d_prev_hop, 0, sizeof(float) * prev_n);   // util.h:275-277: one hop of zeros pre-loaded
   cudaMemset(h->d_tail, 0, sizeof(float) * tail_n);       // util.h:285: calloc'ed out_buff
   int rc = upload_tables(h, h->own_stream);
@@ -514,6 +551,7 @@ extern "C" void bf_destroy(bf_handle* h) {
   cudaFree(h->d_steer_d); cudaFree(h->d_mpf_state); cudaFree(h->d_smooth_hist);
   cudaFree(h->d_sel_slot); cudaFree(h->d_sel_list); cudaFree(h->d_hist); cudaFree(h->d_gss_w); cudaFree(h->d_win_d); cudaFree(h->d_twid_d); cudaFree(h->d_win_f); cudaFree(h->d_twid_f);
   cudaFree(h->d_srp_xs); cudaFree(h->d_srp_tau); cudaFree(h->d_srp_freqs);
+  cudaFree(h->d_gsc_aligned); cudaFree(h->d_gsc_tail); cudaFree(h->d_gsc_state); cudaFree(h->d_gsc_head);
   if (h->h_stage_in) cudaFreeHost(h->h_stage_in);
   if (h->h_stage_out) cudaFreeHost(h->h_stage_out);
   delete h;
@@ -675,7 +713,23 @@ static int run_segment(bf_handle* h, const float* in, size_t ss, size_t ms, floa
   const bool gen_algo = h->cfg.algo == BF_ALGO_DAS || h->cfg.algo == BF_ALGO_PHASE || h->cfg.algo == BF_ALGO_PHASEMPF;
   static const bool force_sel_generic = getenv("BF_SEL_GENERIC") != nullptr;   // debug: cross-check the general gated kernel
   const bool sel_algo = h->cfg.algo == BF_ALGO_MVDR || h->cfg.algo == BF_ALGO_LCMV || h->cfg.algo == BF_ALGO_GSS;
-  if (h->cfg.algo == BF_ALGO_MCRA) CUDA_TRY(bf::launch_frames_kernel_mcra(p, st));
+  if (h->cfg.algo == BF_ALGO_GSC) {
+    const size_t need = (size_t)p.n_streams * h->M * (size_t)(h1 - h0) * h->H;
+    if (need > h->gsc_aligned_cap) {
+      CUDA_TRY(cudaStreamSynchronize(st));
+      if (h->d_gsc_aligned) cudaFree(h->d_gsc_aligned);
+      h->d_gsc_aligned = nullptr; h->gsc_aligned_cap = 0;
+      if (cudaMalloc(&h->d_gsc_aligned, sizeof(float) * need) != cudaSuccess) return fail(BF_ERR_ALLOC, "gsc: aligned-signal workspace");
+      h->gsc_aligned_cap = need;
+    }
+    p.gsc_aligned = h->d_gsc_aligned;
+    p.gsc_aligned_stream_stride = (long long)h->M * (long long)(h1 - h0) * h->H;
+    p.gsc_tail = h->d_gsc_tail; p.gsc_state = h->d_gsc_state; p.gsc_head = h->d_gsc_head;
+    p.gsc_F = h->cfg.filter_size; p.gsc_use_vad = h->cfg.use_vad;
+    p.gsc_vad_threshold = h->cfg.vad_threshold; p.gsc_mu0 = h->cfg.mu0; p.gsc_mu_max = h->cfg.mu_max;
+    CUDA_TRY(bf::launch_gsc(p, st));
+    h->launches++;
+  } else if (h->cfg.algo == BF_ALGO_MCRA) CUDA_TRY(bf::launch_frames_kernel_mcra(p, st));
   else if (h->cfg.algo == BF_ALGO_REF) CUDA_TRY(bf::launch_ref_kernel(p, st));
   else if (sel_algo && (h->N != 1024 || force_sel_generic || (h->M > 8 && h->cfg.algo != BF_ALGO_GSS)))
     CUDA_TRY(bf::launch_frames_kernel_sel(h->cfg.algo, p, st));

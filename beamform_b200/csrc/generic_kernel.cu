@@ -1428,6 +1428,202 @@ cudaError_t launch_ref_kernel(const KernelParams& p, cudaStream_t st) {
   return cudaGetLastError();
 }
 
+// =====================================================================================================================
+// Generalized sidelobe canceller, gsc.cpp:54-197, in two kernels:
+//   gsc_align_kernel   do_overlap_bymic + apply_weights (gsc.cpp:54-75, util.h:347-379): every microphone is windowed,
+//                      transformed, phase-aligned towards the look direction (x_fft *= conj(w), no 1/M), transformed
+//                      back and overlap-added on its own -> aligned[s][m][sample]
+//   gsc_nlms_kernel    the per-sample loop (gsc.cpp:113-183): fixed beamformer (mean), blocking matrix (differences of
+//                      neighbouring microphones), one adaptive FIR per blocking channel, NLMS update with the step
+//                      normalised by the output or the blocking-channel power.  Sequential in time; one WARP per
+//                      stream, taps spread over the lanes, delay lines as rings in shared memory.
+// Float arithmetic of the reference is kept per element (separate multiply and add, same expression order); only
+// the three F-term sums per sample (filter output and the two powers) are formed as per-lane partial sums + a
+// butterfly instead of one sequential chain.
+// =====================================================================================================================
+template <int NN>
+__global__ void __launch_bounds__(kGenThreads, 1) gsc_align_kernel(const __grid_constant__ KernelParams p) {
+  constexpr int H = NN / 2;
+  unsigned char* smem_raw = gen_smem_raw;
+  float2* zall = reinterpret_cast<float2*>(smem_raw);                       // [M][NN]
+  float* tails = reinterpret_cast<float*>(zall + (size_t)p.M * NN);          // [M][H]
+  const int tid = threadIdx.x, M = p.M;
+  const int s = blockIdx.x + p.stream_begin;
+  const float2* tw = p.twid_f;
+  const float* win = p.win_f;
+  for (int i = tid; i < M * H; i += kGenThreads) tails[i] = p.gsc_tail[(size_t)s * M * H + i];
+  __syncthreads();
+  const int nh = p.hop_end - p.hop_begin;
+  const int npairs = (nh + 1) >> 1;
+  const long long mic_stride = (long long)nh * H;
+  for (int ip = 0; ip < npairs; ip++) {
+    const int t = p.hop_begin + 2 * ip;
+    const bool two = t + 1 < p.hop_end;
+    for (int ch = 0; ch < M; ch++) {   // window + pack (util.h:217-242)
+      const float* base = p.in + (size_t)s * p.in_stream_stride + (size_t)ch * p.in_mic_stride;
+      const float* ha = (t - 1 < 0) ? p.prev_hop + ((size_t)s * M + ch) * H : base + (size_t)(t - 1) * H;
+      const float* hb = base + (size_t)t * H;
+      const float* hc = two ? base + (size_t)(t + 1) * H : hb;
+      for (int n = tid; n < H; n += kGenThreads) {
+        const float a = __ldg(ha + n), b = __ldg(hb + n), c = two ? __ldg(hc + n) : 0.f;
+        const float w0 = 0.5f * __ldg(win + n), w1 = 0.5f * __ldg(win + n + H);
+        zall[(size_t)ch * NN + swz(n)] = make_float2(a * w0, (two ? b : 0.f) * w0);
+        zall[(size_t)ch * NN + swz(n + H)] = make_float2(b * w1, c * w1);
+      }
+    }
+    __syncthreads();
+    block_fft_fn<NN, -1, float2>(0u, M, tw, tid);
+    // x_fft[j] *= conj(weights[mic][j]) (gsc.cpp:62-65); the real part taken afterwards keeps the Hermitian part, which
+    // lets both frames of the pair share the transform: G = ceff .* Z, ceff = (conj(w_j) + w_{N-j}) / 2 (host, double)
+    for (int e = tid; e < M * NN; e += kGenThreads) {
+      const int ch = e / NN, j = e - ch * NN;
+      const float2 z = zall[(size_t)ch * NN + swz(j)];
+      const float2 w = __ldg(p.das_ceff + (size_t)ch * NN + j);
+      zall[(size_t)ch * NN + swz(j)] = make_float2(2.0f * (z.x * w.x - z.y * w.y), 2.0f * (z.x * w.y + z.y * w.x));   // Z carries the 0.5 of the packing
+    }
+    __syncthreads();
+    block_fft_fn<NN, 1, float2>(0u, M, tw, tid);
+    for (int ch = 0; ch < M; ch++) {   // util.h:244-253 + the per-microphone overlap-add of util.h:361-363
+      float* o0 = p.gsc_aligned + (size_t)(s - p.stream_begin) * p.gsc_aligned_stream_stride + (size_t)ch * mic_stride + (size_t)(t - p.hop_begin) * H;
+      const float2* res = zall + (size_t)ch * NN;
+      float* tl = tails + ch * H;
+      for (int n = tid; n < H; n += kGenThreads) {
+        const float w0 = __ldg(win + n) * p.out_scale, w1 = __ldg(win + n + H) * p.out_scale;
+        const float2 a = res[swz(n)], b = res[swz(n + H)];
+        o0[n] = tl[n] + a.x * w0;
+        if (two) {
+          o0[H + n] = b.x * w1 + a.y * w0;
+          tl[n] = b.y * w1;
+        } else {
+          tl[n] = b.x * w1;
+        }
+      }
+    }
+    __syncthreads();
+  }
+  for (int i = tid; i < M * H; i += kGenThreads) p.gsc_tail[(size_t)s * M * H + i] = tails[i];
+}
+
+constexpr int kNlmsWarps = 4;
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__global__ void __launch_bounds__(kNlmsWarps * 32) gsc_nlms_kernel(const __grid_constant__ KernelParams p) {
+  extern __shared__ __align__(16) float nlms_smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int sl = blockIdx.x * kNlmsWarps + warp;   // stream inside this launch
+  if (sl >= p.n_streams) return;
+  const int s = sl + p.stream_begin;
+  const int M = p.M, M1 = M - 1, F = p.gsc_F, Q = F / 32;
+  const int per_warp = (2 * M1 + 1) * F + M * 32 + 32;
+  float* blk = nlms_smem + (size_t)warp * per_warp;   // [M1][F] blocking-matrix delay lines (rings)
+  float* flt = blk + M1 * F;                           // [M1][F] filters, by logical tap
+  float* lst = flt + M1 * F;                           // [F] last outputs (ring)
+  float* tile = lst + F;                               // [M][32] aligned samples of the current block of 32
+  float* otile = tile + M * 32;                        // [32] outputs of the block
+  float* st = p.gsc_state + (size_t)s * (2 * M1 + 1) * F;
+  for (int i = lane; i < (2 * M1 + 1) * F; i += 32) blk[i] = st[i];
+  int head = p.gsc_head[s];
+  __syncwarp();
+  const int nh = p.hop_end - p.hop_begin;
+  const long long n_samples = (long long)nh * p.H, mic_stride = n_samples;
+  const float* al = p.gsc_aligned + (size_t)sl * p.gsc_aligned_stream_stride;
+  float* out = p.out + (size_t)s * p.out_stream_stride + (size_t)p.hop_begin * p.H;
+  const float fM = (float)M, fF = (float)F;
+  for (long long base = 0; base < n_samples; base += 32) {
+    for (int i = 0; i < M; i++) tile[i * 32 + lane] = al[(size_t)i * mic_stride + base + lane];
+    __syncwarp();
+    for (int jj = 0; jj < 32; jj++) {
+      // fixed beamformer (gsc.cpp:116-121) and the new blocking-matrix samples (gsc.cpp:124)
+      float das = 0.0f;
+      for (int i = 0; i < M; i++) das = __fadd_rn(das, tile[i * 32 + jj]);
+      float o = __fdiv_rn(das, fM);
+      if (lane < M1) blk[lane * F + head] = __fsub_rn(tile[(lane + 1) * 32 + jj], tile[lane * 32 + jj]);   // shift_data: the oldest slot takes the new sample
+      const int hd = (head + 1 == F) ? 0 : head + 1;   // ring position of logical tap 0 after the shift
+      float keep_pw = 0.f;
+      __syncwarp();
+      // filter outputs and blocking-channel powers (gsc.cpp:127-131, 84-91)
+      for (int i = 0; i < M1; i++) {
+        float dot = 0.f, pw = 0.f;
+        for (int q = 0; q < Q; q++) {
+          const int k = lane + 32 * q;
+          int ph = hd + k; if (ph >= F) ph -= F;
+          const float b = blk[i * F + ph];
+          dot = fmaf(flt[i * F + k], b, dot);
+          pw = fmaf(b, b, pw);
+        }
+        dot = warp_sum(dot);
+        pw = warp_sum(pw);
+        o = __fsub_rn(o, dot);   // out[j] -= block_out
+        if (lane == i) keep_pw = pw;   // the power of channel i is needed once the output is known: parked in lane i
+      }
+      // last outputs and their power (gsc.cpp:138-140)
+      if (lane == 0) lst[head] = o;
+      __syncwarp();
+      float lp = 0.f;
+      for (int q = 0; q < Q; q++) { const float v = lst[lane + 32 * q]; lp = fmaf(v, v, lp); }
+      lp = warp_sum(lp);
+      const float last_out_power = __fsqrt_rn(__fdiv_rn(lp, fF));
+      if ((double)last_out_power < p.gsc_vad_threshold || !p.gsc_use_vad) {
+        for (int i = 0; i < M1; i++) {
+          const float bpw = __shfl_sync(0xffffffffu, keep_pw, i);
+          const float block_power = __fsqrt_rn(__fdiv_rn(bpw, fF));
+          float this_mu;
+          if (p.gsc_mu0 * (double)block_power / (double)last_out_power < p.gsc_mu_max) this_mu = (float)(p.gsc_mu0 / (double)last_out_power);
+          else this_mu = (float)(p.gsc_mu0 / (double)block_power);
+          if (isnan(this_mu) || isinf(this_mu)) this_mu = 0.0f;
+          const float g = __fmul_rn(this_mu, o);
+          for (int q = 0; q < Q; q++) {
+            const int k = lane + 32 * q;
+            int ph = hd + k; if (ph >= F) ph -= F;
+            float f = __fadd_rn(flt[i * F + k], __fmul_rn(g, blk[i * F + ph]));   // filter[i][k] += this_mu*out[j]*block_matrix[i][k]
+            if (isnan(f)) f = 0.0f;
+            flt[i * F + k] = f;
+          }
+        }
+      }
+      if (lane == 0) otile[jj] = o;
+      head = hd;
+      __syncwarp();
+    }
+    out[base + lane] = otile[lane];
+    __syncwarp();
+  }
+  // persist: rings are stored as they are, with their head
+  for (int i = lane; i < (2 * M1 + 1) * F; i += 32) st[i] = blk[i];
+  if (lane == 0) p.gsc_head[s] = head;
+}
+
+template <int NN>
+static cudaError_t launch_gsc_n(const KernelParams& p, cudaStream_t st) {
+  const size_t smem = sizeof(float2) * (size_t)p.M * NN + sizeof(float) * (size_t)p.M * (NN / 2) + 16;
+  cudaError_t e = cudaFuncSetAttribute(gsc_align_kernel<NN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  gsc_align_kernel<NN><<<p.n_streams, kGenThreads, smem, st>>>(p);
+  return cudaGetLastError();
+}
+size_t gsc_align_smem(int N, int M) { return sizeof(float2) * (size_t)M * N + sizeof(float) * (size_t)M * (N / 2) + 16; }
+cudaError_t launch_gsc(const KernelParams& p, cudaStream_t st) {
+  cudaError_t e = cudaErrorNotSupported;
+  switch (p.N) {
+    case 512: e = launch_gsc_n<512>(p, st); break;
+    case 1024: e = launch_gsc_n<1024>(p, st); break;
+    case 2048: e = launch_gsc_n<2048>(p, st); break;
+    case 4096: e = launch_gsc_n<4096>(p, st); break;
+  }
+  if (e != cudaSuccess) return e;
+  const int M1 = p.M - 1;
+  const size_t smem = sizeof(float) * kNlmsWarps * ((size_t)(2 * M1 + 1) * p.gsc_F + (size_t)p.M * 32 + 32);
+  e = cudaFuncSetAttribute(gsc_nlms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  gsc_nlms_kernel<<<(p.n_streams + kNlmsWarps - 1) / kNlmsWarps, kNlmsWarps * 32, smem, st>>>(p);
+  return cudaGetLastError();
+}
+
 template <int NN>
 static size_t gen_smem(int M, bool pha) { return (pha ? sizeof(double2) : sizeof(float2)) * (size_t)M * NN + sizeof(float2) * NN + sizeof(GenScratch<NN>) + 16; }
 

@@ -52,6 +52,9 @@ WORKLOADS = {
                  interferers=(), kernel="frames_kernel_mcra<1024>", alg_channels=1),
     "ref": dict(name="rosjack_ref passthrough (window^2 overlap-add), first microphone of aira3", algo="ref", mics="aira3", n_streams=2368,
                 hops_per_step=188, interferers=(), kernel="ref_kernel", alg_channels=1),
+    # SURVEY.md section 8f rank 1
+    "gsc": dict(name="GSC 3-mic (aira3) 1024-pt: per-microphone alignment + 128-tap NLMS (gsc.launch)", algo="gsc", mics="aira3", n_streams=4736,
+                hops_per_step=94, interferers=(), kernel="gsc_nlms_kernel (+ gsc_align_kernel<1024>)"),
     "ph": dict(name="Phase 3-mic (aira3) 1024-pt phase mask", algo="phase", mics="aira3", n_streams=1184, hops_per_step=188,
                interferers=(), kernel="frames_kernel_1024<phase>"),
 }

@@ -31,6 +31,9 @@ typedef enum bf_algo {
   BF_ALGO_PHASEMPF = 5,
   BF_ALGO_MCRA = 6,   /* stand-alone MCRA noise-reduction node (mcra.cpp:62-155): first microphone only; launch keys
                          alphaS, alphaD, alphaD2, delta, L, out_amp, out_only_noise (launch/mcra.launch) */
+  BF_ALGO_GSC = 8,    /* generalized sidelobe canceller (gsc.cpp:54-197): per-microphone frequency-domain alignment, then a
+                         time-domain NLMS with a power-normalised step; launch keys use_vad, vad_threshold, mu0, mu_max,
+                         filter_size (launch/gsc.launch) */
   BF_ALGO_REF = 7     /* rosjack_ref (jack_ref.cpp:19-60): window^2 overlap-add of the first microphone, the delay-matched
                          reference signal of the evaluation scripts */
 } bf_algo;
@@ -76,6 +79,10 @@ typedef struct bf_config {
   int32_t dropped_hops_on_restructure; /* hops lost while READY=false after an interference add/remove
                                           (lcmv.cpp:271-276 sleeps 30 ms); default 0 */
   int32_t device;                      /* CUDA device ordinal */
+  /* gsc (gsc.cpp:206-258); appended so that older callers' layouts stay valid */
+  int32_t use_vad;
+  double vad_threshold, mu0, mu_max;
+  int32_t filter_size;                 /* NLMS taps per blocking-matrix channel: multiple of 32, <= 256 */
 } bf_config;
 
 /* The two control topics, scheduled offline: applied atomically BEFORE hop `hop_index` is processed. */

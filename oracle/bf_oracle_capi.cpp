@@ -28,6 +28,9 @@ typedef struct bfo_config {
   double MPF_alphaS, MPF_eta, MPF_rev_gamma, MPF_rev_delta;
   double noise_floor;
   int32_t out_only_noise, out_only_mcra;
+  int32_t use_vad;
+  double vad_threshold, mu0, mu_max;
+  int32_t filter_size;
 } bfo_config;
 
 typedef struct bfo_event {
@@ -52,6 +55,7 @@ static bfo::Config to_cfg(const bfo_config* c) {
   k.MCRA_delta = c->MCRA_delta; k.MCRA_L = c->MCRA_L; k.MPF_alphaS = c->MPF_alphaS; k.MPF_eta = c->MPF_eta;
   k.MPF_rev_gamma = c->MPF_rev_gamma; k.MPF_rev_delta = c->MPF_rev_delta; k.noise_floor = c->noise_floor;
   k.out_only_noise = c->out_only_noise != 0; k.out_only_mcra = c->out_only_mcra != 0;
+  k.use_vad = c->use_vad != 0; k.vad_threshold = c->vad_threshold; k.mu0 = c->mu0; k.mu_max = c->mu_max; k.filter_size = c->filter_size;
   return k;
 }
 

@@ -22,6 +22,9 @@ CASES = {
     "mcra_binaural_hop2048_only_noise": dict(algo="mcra", mics="binaural", hops=60, seed=115, hop=2048, synth=dict(gate_hz=1.3), cfg=dict(L=20, out_only_noise=True)),
     "ref_aira3": dict(algo="ref", mics="aira3", hops=40, seed=116),
     "ref_circ8_hop256": dict(algo="ref", mics="circ8", hops=48, seed=117, hop=256),
+    # generalized sidelobe canceller (launch/gsc.launch)
+    "gsc_aira3_theta_event": dict(algo="gsc", mics="aira3", hops=60, seed=118, events=[(25, "theta", 20.0)]),
+    "gsc_circ8_hop256_vad": dict(algo="gsc", mics="circ8", hops=80, seed=119, hop=256, cfg=dict(initial_angle=-35.0, use_vad=True, vad_threshold=0.08, filter_size=64)),
 }
 
 

@@ -25,6 +25,7 @@ class BfoConfig(C.Structure):
         ("MCRA_L", C.c_int32),
         ("MPF_alphaS", C.c_double), ("MPF_eta", C.c_double), ("MPF_rev_gamma", C.c_double), ("MPF_rev_delta", C.c_double),
         ("noise_floor", C.c_double), ("out_only_noise", C.c_int32), ("out_only_mcra", C.c_int32),
+        ("use_vad", C.c_int32), ("vad_threshold", C.c_double), ("mu0", C.c_double), ("mu_max", C.c_double), ("filter_size", C.c_int32),
     ]
 
 

@@ -21,12 +21,13 @@ NODE_KEYS = {
                  "MPF_alphaS", "MPF_eta", "MPF_rev_gamma", "MPF_rev_delta", "out_amp", "noise_floor", "out_only_noise", "out_only_mcra"],
     "mcra": ["alphaS", "alphaD", "alphaD2", "delta", "L", "out_amp", "out_only_noise"],
     "ref": [],
+    "gsc": ["use_vad", "vad_threshold", "mu0", "mu_max", "filter_size"],
 }
 # rosparam name -> config field where they differ (the mcra node drops the MCRA_ prefix, mcra.cpp:181-224)
 KEY_FIELD = {"alphaS": "MCRA_alphaS", "alphaD": "MCRA_alphaD", "alphaD2": "MCRA_alphaD2", "delta": "MCRA_delta", "L": "MCRA_L", "lambda": "lambda_"}
 BINARY = {"ref": "jack_ref_ref"}
-INT_KEYS = {"past_windows", "smooth_size", "MCRA_L", "L"}
-BOOL_KEYS = {"out_only_noise", "out_only_mcra"}
+INT_KEYS = {"past_windows", "smooth_size", "MCRA_L", "L", "filter_size"}
+BOOL_KEYS = {"out_only_noise", "out_only_mcra", "use_vad"}
 
 
 def available(algo="das"):

@@ -272,6 +272,25 @@ def test_mcra_and_ref_nodes_match_oracle(algo, mics, hop, kw):
     assert err <= (0.0 if algo == "ref" else REL_L2_TOL)   # rosjack_ref is elementwise float arithmetic: bit-exact
 
 
+@pytest.mark.parametrize("mics,hop,kw,events", [("aira3", 512, {}, ((20, "theta", 25.0),)), ("circ8", 256, dict(initial_angle=-35.0, filter_size=64), ()),
+                                                ("binaural", 2048, dict(use_vad=True, vad_threshold=0.08), ()), ("circ12", 512, dict(filter_size=256, mu0=0.0005, mu_max=0.01), ())])
+def test_gsc_matches_oracle(mics, hop, kw, events):
+    """generalized sidelobe canceller (gsc.cpp): per-microphone alignment + NLMS, state carried across calls."""
+    cfg = bf.make_config("gsc", mics=mics, hop=hop, **kw)
+    n_hops = 70
+    x = np.stack([synth_stream(bf.GEOMETRIES[mics], n_hops * hop, seed=700 + b) for b in range(3)])
+    ref = oracle_batch(cfg, x, events=events)
+    b = bf.Beamformer(cfg, n_streams=3)
+    if events:
+        got = b.process(x, events=events)
+    else:
+        k = 20 * hop
+        got = np.concatenate([b.process(x[:, :, :k]), b.process(x[:, :, k:k + hop]), b.process(x[:, :, k + hop:])], axis=1)
+    err = finite_rel_l2(got, ref)
+    print("gsc", mics, "hop", hop, kw, "rel_l2", err)
+    assert err <= REL_L2_TOL
+
+
 def test_unsupported_shapes_fail_loudly():
     with pytest.raises(bf.BeamformError):
         bf.Beamformer(bf.make_config("mvdr", mics="circ8", hop=2048), 1)      # 8 x 4096-point spectra exceed shared memory
