@@ -755,7 +755,9 @@ static int run_segment(bf_handle* h, const float* in, size_t ss, size_t ms, floa
 
 extern "C" int bf_process_batch_device(bf_handle* h, const float* in, size_t ss, size_t ms, float* out, size_t os, uint32_t n_hops,
                                        const bf_event* ev, uint32_t n_ev, void* cuda_stream) {
-  if (!h || !in || !out) return fail(BF_ERR_INVALID, "bf_process_batch_device: null argument");
+  if (!h) return fail(BF_ERR_INVALID, "bf_process_batch_device: null handle");
+  if (n_hops == 0) return BF_OK;   // an empty batch is a no-op (numpy hands out null data pointers for empty arrays)
+  if (!in || !out) return fail(BF_ERR_INVALID, "bf_process_batch_device: null argument");
   CUDA_TRY(cudaSetDevice(h->dev));
   cudaStream_t st = (cudaStream_t)cuda_stream;
   drain_pending(h);
@@ -802,7 +804,9 @@ static int ensure_io_staging(bf_handle* h, size_t in_floats, size_t out_floats) 
 // (copy-in / compute / copy-out) so PCIe transfers overlap the kernels.
 extern "C" int bf_process_batch(bf_handle* h, const float* in_host, size_t ss, size_t ms, float* out_host, size_t os,
                                 uint32_t n_hops, const bf_event* ev, uint32_t n_ev) {
-  if (!h || !in_host || !out_host) return fail(BF_ERR_INVALID, "bf_process_batch: null argument");
+  if (!h) return fail(BF_ERR_INVALID, "bf_process_batch: null handle");
+  if (n_hops == 0) return BF_OK;   // an empty batch is a no-op
+  if (!in_host || !out_host) return fail(BF_ERR_INVALID, "bf_process_batch: null argument");
   CUDA_TRY(cudaSetDevice(h->dev));
   const size_t L = (size_t)n_hops * h->H;
   int rc = ensure_io_staging(h, (size_t)h->B * h->M * L, (size_t)h->B * L);

@@ -1533,7 +1533,8 @@ __global__ void __launch_bounds__(kNlmsWarps * 32) gsc_nlms_kernel(const __grid_
   const long long n_samples = (long long)nh * p.H, mic_stride = n_samples;
   const float* al = p.gsc_aligned + (size_t)sl * p.gsc_aligned_stream_stride;
   float* out = p.out + (size_t)s * p.out_stream_stride + (size_t)p.hop_begin * p.H;
-  const float fM = (float)M, fF = (float)F;
+  const float fM = (float)M, fF = (float)F, invF = 1.0f / (float)F;
+  const bool pow2F = (F & (F - 1)) == 0;   // then the division by F is an exact scaling
   for (long long base = 0; base < n_samples; base += 32) {
     for (int i = 0; i < M; i++) tile[i * 32 + lane] = al[(size_t)i * mic_stride + base + lane];
     __syncwarp();
@@ -1567,15 +1568,18 @@ __global__ void __launch_bounds__(kNlmsWarps * 32) gsc_nlms_kernel(const __grid_
       float lp = 0.f;
       for (int q = 0; q < Q; q++) { const float v = lst[lane + 32 * q]; lp = fmaf(v, v, lp); }
       lp = warp_sum(lp);
-      const float last_out_power = __fsqrt_rn(__fdiv_rn(lp, fF));
+      const float last_out_power = __fsqrt_rn(pow2F ? lp * invF : __fdiv_rn(lp, fF));
       if ((double)last_out_power < p.gsc_vad_threshold || !p.gsc_use_vad) {
+        // step sizes (gsc.cpp:147-156): lane i owns channel i, so the double-precision quotients are formed once per
+        // sample instead of once per channel by every lane.  mu0 / last_out_power is shared by all channels.
+        const float bpw = keep_pw;
+        const float block_power = __fsqrt_rn(pow2F ? bpw * invF : __fdiv_rn(bpw, fF));
+        float my_mu;
+        if (p.gsc_mu0 * (double)block_power / (double)last_out_power < p.gsc_mu_max) my_mu = (float)(p.gsc_mu0 / (double)last_out_power);
+        else my_mu = (float)(p.gsc_mu0 / (double)block_power);
+        if (isnan(my_mu) || isinf(my_mu)) my_mu = 0.0f;
         for (int i = 0; i < M1; i++) {
-          const float bpw = __shfl_sync(0xffffffffu, keep_pw, i);
-          const float block_power = __fsqrt_rn(__fdiv_rn(bpw, fF));
-          float this_mu;
-          if (p.gsc_mu0 * (double)block_power / (double)last_out_power < p.gsc_mu_max) this_mu = (float)(p.gsc_mu0 / (double)last_out_power);
-          else this_mu = (float)(p.gsc_mu0 / (double)block_power);
-          if (isnan(this_mu) || isinf(this_mu)) this_mu = 0.0f;
+          const float this_mu = __shfl_sync(0xffffffffu, my_mu, i);
           const float g = __fmul_rn(this_mu, o);
           for (int q = 0; q < Q; q++) {
             const int k = lane + 32 * q;

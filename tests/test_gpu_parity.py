@@ -291,6 +291,59 @@ def test_gsc_matches_oracle(mics, hop, kw, events):
     assert err <= REL_L2_TOL
 
 
+# ---------------------------------------------------------------------------------------------
+# the drop-in boundary itself: bf_process_hop is the body of jack_callback (das.cpp:72-92) for every node
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("algo,mics,kw,setters", [
+    ("mvdr", "circ8", {}, ()), ("lcmv", "circ8", dict(interferers=(80.0, -60.0, 150.0)), ((9, "interf", 2, -55.0), (15, "interf", 4, 120.0))),
+    ("gss", "aira3", {}, ((12, "theta", 25.0),)), ("phase", "aira3", dict(mag_threshold=0.002), ()), ("phasempf", "binaural", {}, ()),
+    ("mcra", "aira3", dict(L=10), ()), ("ref", "aira3", {}, ()), ("gsc", "aira3", {}, ((12, "theta", 25.0),))])
+def test_hop_at_a_time_callback_matches_oracle_for_every_node(algo, mics, kw, setters):
+    cfg = bf.make_config(algo, mics=mics, **kw)
+    n_hops = 30
+    x = synth_stream(bf.GEOMETRIES[mics], n_hops * H, seed=800)
+    ref = Oracle(cfg).process(x, events=setters)
+    b = bf.Beamformer(cfg, n_streams=1)
+    outs = []
+    for t in range(n_hops):
+        for e in setters:   # the ROS callbacks (theta_roscallback / interf_theta_roscallback) arrive between two JACK periods
+            if e[0] == t:
+                b.set_theta(e[2]) if e[1] == "theta" else b.set_interference(e[2], e[3])
+        outs.append(b.process_hop(x[:, t * H:(t + 1) * H]))
+    got = np.concatenate(outs)
+    err = finite_rel_l2(got, ref)
+    print(algo, "hop-at-a-time rel_l2", err)
+    assert err <= REL_L2_TOL
+
+
+@pytest.mark.parametrize("algo,mics", [("das", "aira3"), ("mvdr", "circ8"), ("phasempf", "binaural"), ("gsc", "aira3")])
+def test_empty_and_ragged_batches(algo, mics):
+    """0 hops is a no-op; odd hop counts (a frame pair cut in half) and 1-hop calls give the same stream as one call."""
+    cfg = bf.make_config(algo, mics=mics)
+    x = np.stack([synth_stream(bf.GEOMETRIES[mics], 23 * H, seed=810 + b) for b in range(2)])
+    ref = oracle_batch(cfg, x)
+    b = bf.Beamformer(cfg, n_streams=2)
+    assert b.process(x[:, :, :0]).shape == (2, 0)
+    cuts = [0, 1, 4, 9, 10, 23]   # 1, 3, 5, 1, 13 hops
+    got = np.concatenate([b.process(x[:, :, a * H:c * H]) for a, c in zip(cuts[:-1], cuts[1:])], axis=1)
+    assert finite_rel_l2(got, ref) <= REL_L2_TOL
+
+
+def test_two_handles_are_independent():
+    """Per-handle state only (the reference keeps its state in process globals): two nodes interleaved on one device."""
+    cfg_a, cfg_b = bf.make_config("mvdr", mics="circ8"), bf.make_config("phasempf", mics="binaural")
+    xa = synth_stream(bf.GEOMETRIES["circ8"], 20 * H, seed=820)[None]
+    xb = synth_stream(bf.GEOMETRIES["binaural"], 20 * H, seed=821)[None]
+    a, b = bf.Beamformer(cfg_a, 1), bf.Beamformer(cfg_b, 1)
+    ga = np.concatenate([a.process(xa[:, :, :8 * H]), a.process(xa[:, :, 8 * H:])], axis=1) if False else None
+    pa, pb = [], []
+    for k in range(0, 20, 4):
+        pa.append(a.process(xa[:, :, k * H:(k + 4) * H]))
+        pb.append(b.process(xb[:, :, k * H:(k + 4) * H]))
+    assert finite_rel_l2(np.concatenate(pa, axis=1), oracle_batch(cfg_a, xa)) <= REL_L2_TOL
+    assert finite_rel_l2(np.concatenate(pb, axis=1), oracle_batch(cfg_b, xb)) <= REL_L2_TOL
+
+
 def test_unsupported_shapes_fail_loudly():
     with pytest.raises(bf.BeamformError):
         bf.Beamformer(bf.make_config("mvdr", mics="circ8", hop=2048), 1)      # 8 x 4096-point spectra exceed shared memory
