@@ -50,7 +50,8 @@ typedef enum bf_status {
 /*
  * Everything the reference reads from the ROS parameter server and from JACK, under the same
  * names.  bf_config_init() fills the getParam fall-backs of the chosen node
- * (mvdr.cpp:146-187, lcmv.cpp:170-219, gss.cpp:177-240, phase.cpp:166-191, phasempf.cpp:357-473);
+ * (mvdr.cpp:146-187, lcmv.cpp:170-219, gss.cpp:177-240, phase.cpp:166-191, phasempf.cpp:357-473,
+ * gsc.cpp:206-258, mcra.cpp:177-226);
  * bf_config_load_yaml() reads beamform_config.yaml (util.h:52-113); bf_config_set() takes one
  * launch-file <rosparam> key (launch/xxx.launch).
  */
