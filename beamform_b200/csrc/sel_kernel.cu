@@ -12,13 +12,15 @@
 //       magnitude gate with a guard band, append both frames to the per-stream history ring (global, L2-resident:
 //       ring depth P+2 so a pair's two appends never overwrite a frame its own solves still need), default outputs
 //   B1b guarded bins are re-decided in FP64 (exact double DFT of that bin) -> bit-exact selected-bin set
-//   B2  thread per selected (bin, frame): covariance of the previous P frames, Cholesky, MVDR / LCMV weights (or
-//       the GSS recursion, thread per bin); the LAST warp first runs the inverse FFT + overlap-add of the PREVIOUS
-//       pair, which hides the one transform that has no peer inside the solves' slack
+//   B2  lane pair per selected bin (one lane per frame of the pair): the P-1 history frames the two frames share are
+//       summed once (half per lane + one shfl.xor), each lane adds the frame only its own history holds, Cholesky,
+//       MVDR / LCMV weights (GSS: thread per bin, its recursion is sequential); ring frames arrive through a
+//       per-thread cp.async pipeline; the LAST warp first runs the inverse FFT + overlap-add of the PREVIOUS pair
 //   B3  Hermitian assembly of G = Yh_t + i*Yh_{t+1} for the next inverse
 // Spectra never leave the SM except for the history ring the algorithm itself keeps (mvdr.cpp:99-101).
 #include <cstdio>
 #include <cstdlib>
+#include <type_traits>
 
 #include "async_copy.cuh"
 #include "bf_device.h"
@@ -103,15 +105,20 @@ struct RingPipe {
   const float2* ring_l;   // &ring[slot 0][mic 0][this bin]
   float2* my;             // this thread's staging slots
   size_t mic_stride, slot_stride;
-  int M, D, P;
-  int next_k, next_ring, next_stage, read_stage;
+  int M, D;
+  // request schedule, as frame offsets from frame t-P (ring slot slot_base): n_sh shared history frames starting at sh_off,
+  // then (n_req > n_sh) the thread's own extra history frame and its own frame x
+  int slot_base, n_sh, sh_off, extra_off, x_off, n_req;
+  int next_k, next_stage, read_stage;
   __device__ __forceinline__ void issue() {   // request frame next_k (if any) and close one cp.async group either way
-    if (next_k <= P) {
-      const float2* src = ring_l + (size_t)next_ring * slot_stride;
+    if (next_k < n_req) {
+      const int off = next_k < n_sh ? sh_off + next_k : (next_k == n_sh ? extra_off : x_off);
+      int ring = slot_base + off;
+      if (ring >= D) ring -= D;
+      const float2* src = ring_l + (size_t)ring * slot_stride;
       float2* dst = my + next_stage * M;
       for (int i = 0; i < M; i++)
         asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst + i)), "l"(src + (size_t)i * mic_stride) : "memory");
-      if (++next_ring == D) next_ring = 0;
       if (++next_stage == kStageDepth) next_stage = 0;
     }
     next_k++;
@@ -132,10 +139,31 @@ struct RingPipe {
   }
 };
 
-// Covariance of the P frames before the item's frame (mvdr.cpp:87, :239-243), its Cholesky factor, and the item's
-// own frame x (the last stage of the pipeline).
+template <int MM, typename T>
+__device__ __forceinline__ void cov_rank1(HermLower<MM, T>& A, const float2 (&hf)[MM]) {
+  typedef HermLower<MM, T> HL;
+  cplx<T> h[MM];
+#pragma unroll
+  for (int i = 0; i < MM; i++) h[i] = mk<T>((T)hf[i].x, (T)hf[i].y);
+#pragma unroll
+  for (int i = 0; i < MM; i++) {
+    A.dg[i] = fma_t<T>(h[i].x, h[i].x, fma_t<T>(h[i].y, h[i].y, A.dg[i]));
+#pragma unroll
+    for (int j = 0; j < i; j++) {   // h_i * conj(h_j)
+      cplx<T>& r = A.lo[HL::idx(i, j)];
+      r.x = fma_t<T>(h[i].x, h[j].x, fma_t<T>(h[i].y, h[j].y, r.x));
+      r.y = fma_t<T>(h[i].y, h[j].x, fma_t<T>(-h[i].x, h[j].y, r.y));
+    }
+  }
+}
+
+// Covariance for the two frames (t, t+1) of one bin by a PAIR of adjacent lanes (lane parity f = frame).  The histories
+// of the two frames share P-1 frames (t-P+1 .. t-1): each lane accumulates half of them, one butterfly step (shfl.xor 1)
+// gives both the full shared sum, then a selected lane adds the one frame only its own history holds (t-P for frame t,
+// t for frame t+1; mvdr.cpp:87, :239-243), factorises and keeps its own frame x.  All 32 lanes of the warp call this
+// (inactive ones with an empty schedule) so that the shuffle is unconditional.  Returns with the Cholesky factor in A.
 template <int MM, typename T, class Pipe>
-__device__ __forceinline__ void ring_cov_chol(const KernelParams& p, HermLower<MM, T>& A, T (&invd)[MM], Pipe& pipe, float2 (&x)[MM]) {
+__device__ __forceinline__ void pair_cov_chol(const KernelParams& p, HermLower<MM, T>& A, T (&invd)[MM], Pipe& pipe, bool sel, float2 (&x)[MM]) {
   typedef HermLower<MM, T> HL;
   const int M = p.M;
 #pragma unroll
@@ -144,26 +172,29 @@ __device__ __forceinline__ void ring_cov_chol(const KernelParams& p, HermLower<M
   for (int i = 0; i < MM * (MM - 1) / 2; i++) A.lo[i] = mk<T>(T(0), T(0));
   pipe.start();
 #pragma unroll 1
-  for (int k = 0; k < p.P; k++) {
+  for (int k = 0; k < pipe.n_sh; k++) {
     float2 hf[MM];
     pipe.template take<MM>(hf);
-    cplx<T> h[MM];
-#pragma unroll
-    for (int i = 0; i < MM; i++) h[i] = mk<T>((T)hf[i].x, (T)hf[i].y);
-#pragma unroll
-    for (int i = 0; i < MM; i++) {
-      A.dg[i] = fma_t<T>(h[i].x, h[i].x, fma_t<T>(h[i].y, h[i].y, A.dg[i]));
-#pragma unroll
-      for (int j = 0; j < i; j++) {   // h_i * conj(h_j)
-        cplx<T>& r = A.lo[HL::idx(i, j)];
-        r.x = fma_t<T>(h[i].x, h[j].x, fma_t<T>(h[i].y, h[j].y, r.x));
-        r.y = fma_t<T>(h[i].y, h[j].x, fma_t<T>(-h[i].x, h[j].y, r.y));
-      }
-    }
+    cov_rank1<MM, T>(A, hf);
     pipe.issue();   // into the slot just consumed
   }
-  pipe.template take<MM>(x);
+  __syncwarp();
+#pragma unroll
+  for (int i = 0; i < MM; i++) A.dg[i] += __shfl_xor_sync(0xffffffffu, A.dg[i], 1);
+#pragma unroll
+  for (int i = 0; i < MM * (MM - 1) / 2; i++) {
+    A.lo[i].x += __shfl_xor_sync(0xffffffffu, A.lo[i].x, 1);
+    A.lo[i].y += __shfl_xor_sync(0xffffffffu, A.lo[i].y, 1);
+  }
+  if (sel) {
+    float2 hf[MM];
+    pipe.template take<MM>(hf);
+    cov_rank1<MM, T>(A, hf);
+    pipe.issue();
+    pipe.template take<MM>(x);
+  }
   asm volatile("cp.async.wait_group 0;" ::: "memory");
+  if (!sel) return;
 #pragma unroll
   for (int j = 0; j < MM; j++) {
     if (j < M) {
@@ -192,12 +223,9 @@ __device__ __forceinline__ void ring_cov_chol(const KernelParams& p, HermLower<M
 }
 
 // mvdr.cpp:86-94 with R = L L^H: z = L^{-1} d, u = L^{-1} x, y = (z^H u) / (z^H z)
-template <int MM, typename T, class Pipe>
-__device__ __forceinline__ float2 mvdr_ring_item(const KernelParams& p, Pipe& pipe, const float2* steer_l) {
-  HermLower<MM, T> A;
-  T invd[MM];
-  float2 x[MM];
-  ring_cov_chol<MM, T>(p, A, invd, pipe, x);
+template <int MM, typename T>
+__device__ __forceinline__ float2 mvdr_finish(const KernelParams& p, const HermLower<MM, T>& A, const T (&invd)[MM], const float2 (&x)[MM],
+                                              const float2* steer_l) {
   cplx<T> z[MM], u[MM];
 #pragma unroll
   for (int i = 0; i < MM; i++) {
@@ -234,12 +262,9 @@ __device__ __forceinline__ float2 mvdr_ring_item(const KernelParams& p, Pipe& pi
 
 // lcmv.cpp:111-119: W = R^{-1} C (C^H R^{-1} C)^{-1}, y = W(:,0)^H x.  V = L^{-1} C, u = L^{-1} x, G = V^H V, b = V^H u,
 // y = g^H b with G g = e_0.
-template <int MM, typename T, class Pipe>
-__device__ __forceinline__ float2 lcmv_ring_item(const KernelParams& p, Pipe& pipe, const float2* steer_l) {
-  HermLower<MM, T> A;
-  T invd[MM];
-  float2 x[MM];
-  ring_cov_chol<MM, T>(p, A, invd, pipe, x);
+template <int MM, typename T>
+__device__ __forceinline__ float2 lcmv_finish(const KernelParams& p, const HermLower<MM, T>& A, const T (&invd)[MM], const float2 (&x)[MM],
+                                              const float2* steer_l) {
   const int C = p.C, M = p.M;
   cplx<T> u[MM];
 #pragma unroll
@@ -476,15 +501,15 @@ __global__ void __launch_bounds__(kSelThreads, ALGO == ALGO_LCMV ? 1 : 2) sel_pa
       }
     }
     __syncthreads();
-    // work list: runs of consecutive bins stay contiguous, so neighbouring threads of B2 read neighbouring
-    // ring addresses.  mvdr/lcmv: one item per selected (bin, frame); gss: one per bin (its recursion is
-    // sequential over the frames of a bin).
+    // work list: one item per bin selected in either frame; runs of consecutive bins stay contiguous, so neighbouring
+    // threads of B2 read neighbouring ring addresses.  mvdr/lcmv: a lane pair per item (one lane per frame, the shared
+    // part of the two histories summed once); gss: one thread per item (its recursion is sequential over the frames).
     if (live) {
-      for (int f = 0; f < (ALGO == ALGO_GSS ? 1 : nf); f++)
+      for (int f = 0; f < 1; f++)
         for (int base = warp * 32; base < kL1K; base += kSelThreads) {
           const int l = base + lane;
           bool on = false;
-          if (l < kL1K) on = (ALGO == ALGO_GSS) ? ((sc.flag[0][l] | sc.flag[1][l]) != 0) : (sc.flag[f][l] != 0);
+          if (l < kL1K) on = (sc.flag[0][l] | sc.flag[1][l]) != 0;
           const unsigned m = __ballot_sync(0xffffffffu, on);
           int pos = 0;
           if (lane == 0 && m) pos = atomicAdd(&sc.n_items, __popc(m));
@@ -542,32 +567,47 @@ __global__ void __launch_bounds__(kSelThreads, ALGO == ALGO_LCMV ? 1 : 2) sel_pa
     }
     if (live && ALGO != ALGO_GSS) {
       // mvdr / lcmv.  The spectrum tiles are dead after B1 (the current frame is in the ring too), so they become the
-      // per-thread staging slots of the ring pipeline (RingPipe): one item per thread, all threads at once.
+      // per-thread staging slots of the ring pipeline (RingPipe); lane pair (2i, 2i+1) carries item i of the batch.
       const int n_items = sc.n_items;
-      for (int base = 0; base < n_items; base += kSelThreads) {
-        const int nb = min(n_items - base, kSelThreads);
-        const int cap = (kSelWarps * 1024) / nb;             // float2 of staging per item of this batch
-        const int q = base + tid;
+      constexpr int kPairs = kSelThreads / 2;
+      const int n_sh_tot = p.P - 1, n_sh0 = (n_sh_tot + 1) / 2;   // shared history frames; lane 0 takes the first n_sh0
+      for (int base = 0; base < n_items; base += kPairs) {
+        const int nbp = min(n_items - base, kPairs);         // items (pairs) in this batch
+        if (warp * 32 >= 2 * nbp) continue;                  // warp-uniform: no item in this warp
+        const int cap = (kSelWarps * 1024) / (2 * nbp);      // float2 of staging per thread of this batch
+        const int q = base + (tid >> 1), f = tid & 1;
+        const bool on = q < n_items;
         auto run = [&](auto depth_c) {
           constexpr int kDepth = decltype(depth_c)::value;
           const int pitch = (kDepth * M) | 1;                // odd pitch in float2: conflict-free 8-byte accesses
-          if (q < n_items) {
-            const int l = sc.items[q] >> 1, f = sc.items[q] & 1;
-            RingPipe<kDepth> pipe;
-            pipe.ring_l = p.hist + (size_t)s * D * M * p.Lsel + sc.sel_slot[l];
-            pipe.my = ztiles + (size_t)tid * pitch;
-            pipe.mic_stride = (size_t)p.Lsel;
-            pipe.slot_stride = (size_t)M * p.Lsel;
-            pipe.M = M; pipe.D = D; pipe.P = p.P;
-            int slot = (fr0 + f - p.P) % D;                  // ring slot of frame (t+f) - P
-            if (slot < 0) slot += D;
-            pipe.next_k = 0; pipe.next_ring = slot; pipe.next_stage = 0; pipe.read_stage = 0;
+          const int l = on ? (sc.items[q] >> 1) : 0;
+          const bool sel = on && sc.flag[f][l] != 0;
+          RingPipe<kDepth> pipe;
+          pipe.ring_l = p.hist + (size_t)s * D * M * p.Lsel + (on ? sc.sel_slot[l] : 0);
+          pipe.my = ztiles + (size_t)tid * pitch;
+          pipe.mic_stride = (size_t)p.Lsel;
+          pipe.slot_stride = (size_t)M * p.Lsel;
+          pipe.M = M; pipe.D = D;
+          int slot = (fr0 - p.P) % D;                        // ring slot of frame t - P
+          if (slot < 0) slot += D;
+          pipe.slot_base = slot;
+          pipe.n_sh = on ? (f ? n_sh_tot - n_sh0 : n_sh0) : 0;
+          pipe.sh_off = f ? 1 + n_sh0 : 1;                   // shared frames are t-P+1 .. t-1
+          pipe.extra_off = f ? p.P : 0;                      // frame t+1 also has frame t, frame t also has frame t-P
+          pipe.x_off = p.P + f;
+          pipe.n_req = pipe.n_sh + (sel ? 2 : 0);
+          pipe.next_k = 0; pipe.next_stage = 0; pipe.read_stage = 0;
+          typedef typename std::conditional<ALGO == ALGO_MVDR, float, double>::type T;
+          HermLower<8, T> A;
+          T invd[8];
+          float2 x[8];
+          pair_cov_chol<8, T>(p, A, invd, pipe, sel, x);
+          if (sel) {
             const float2* steer_l = p.steer + (size_t)l * p.C * M;
-            sc.y[f][l] = (ALGO == ALGO_MVDR) ? mvdr_ring_item<8, float>(p, pipe, steer_l) : lcmv_ring_item<8, double>(p, pipe, steer_l);
+            sc.y[f][l] = (ALGO == ALGO_MVDR) ? mvdr_finish<8, T>(p, A, invd, x, steer_l) : lcmv_finish<8, T>(p, A, invd, x, steer_l);
           }
         };
-        if (cap > 11 * M) run(IC<11>{});                     // P + 1 <= 11 frames at once is the common launch value (P = 10)
-        else if (cap > 6 * M) run(IC<6>{});
+        if (cap > 7 * M) run(IC<7>{});                       // at most ceil((P-1)/2) + 2 = 7 frames per thread at P = 10: all in flight
         else run(IC<3>{});
       }
     }
