@@ -817,7 +817,9 @@ extern "C" int bf_process_batch(bf_handle* h, const float* in_host, size_t ss, s
   if (n_ev == 0 && h->drop_left == 0 && h->B >= 16) {
     rc = upload_tables(h, h->own_stream);
     if (rc != BF_OK) return rc;
-    const uint32_t nchunk = 8, per = (h->B + nchunk - 1) / nchunk;
+    // gsc: the NLMS is one warp per stream and sequential in time, so a launch costs the same for 100 or 4 000 streams:
+    // splitting the batch would multiply its time, not overlap it
+    const uint32_t nchunk = (h->cfg.algo == BF_ALGO_GSC) ? 1 : 8, per = (h->B + nchunk - 1) / nchunk;
     for (uint32_t c = 0, s0 = 0; s0 < h->B; c++, s0 += per) {
       const uint32_t ns = std::min(per, h->B - s0);
       if (dense) {
