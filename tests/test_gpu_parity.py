@@ -344,6 +344,55 @@ def test_two_handles_are_independent():
     assert finite_rel_l2(np.concatenate(pb, axis=1), oracle_batch(cfg_b, xb)) <= REL_L2_TOL
 
 
+# ---------------------------------------------------------------------------------------------
+# BASELINE.json's full sizes: size-independent properties + spot checks against the oracle
+# ---------------------------------------------------------------------------------------------
+def _full_size_case(algo, mics, n_streams, n_hops, hop, spot, **kw):
+    """Runs the bench-shaped batch twice (streams in order, then reversed) on device-resident data:
+       * a stream's output depends on that stream's input only: the reversed batch gives the reversed output, bit for bit
+         (streams land on other SMs / warps / batch slots, so this also checks that no state leaks between streams);
+       * `spot` streams are compared with the CPU oracle at the full length."""
+    import torch
+    from bench import device_synth
+    dev = torch.device("cuda", 0)
+    cfg = bf.make_config(algo, mics=mics, hop=hop, **kw)
+    xy = bf.GEOMETRIES[mics]
+    L = n_hops * hop
+    x = device_synth(torch, xy, n_streams, L, seed=0xBEA4F0, device=dev)
+    y = torch.empty((n_streams, L), dtype=torch.float32, device=dev)
+    st = torch.cuda.current_stream().cuda_stream
+    bf.Beamformer(cfg, n_streams=n_streams).process_device(x.data_ptr(), y.data_ptr(), n_hops, stream_ptr=st)
+    torch.cuda.synchronize()
+    xr = torch.flip(x, dims=[0]).contiguous()
+    yr = torch.empty_like(y)
+    bf.Beamformer(cfg, n_streams=n_streams).process_device(xr.data_ptr(), yr.data_ptr(), n_hops, stream_ptr=st)
+    torch.cuda.synchronize()
+    same = torch.equal(torch.nan_to_num(torch.flip(yr, dims=[0]), nan=12345.0), torch.nan_to_num(y, nan=12345.0))
+    assert same, "a stream's output must not depend on its position in the batch"
+    for sidx in spot:
+        ref = Oracle(cfg).process(x[sidx].cpu().numpy())
+        err = finite_rel_l2(y[sidx].cpu().numpy(), ref)
+        print(algo, "full size, stream", sidx, "rel_l2", err)
+        assert err <= REL_L2_TOL
+
+
+def test_full_size_c1_das():
+    _full_size_case("das", "aira3", 2048, 188, 512, spot=(0, 777, 2047))
+
+
+def test_full_size_c2_mvdr_batched_1k_streams():
+    _full_size_case("mvdr", "circ8", 1184, 188, 512, spot=(0, 1183))
+
+
+def test_full_size_c3_lcmv_and_gss():
+    _full_size_case("lcmv", "circ8", 592, 94, 512, spot=(5,), interferers=(80.0, -60.0, 150.0))
+    _full_size_case("gss", "circ8", 592, 94, 512, spot=(5,), interferers=(80.0, -60.0, 150.0))
+
+
+def test_full_size_c4_phasempf_4096():
+    _full_size_case("phasempf", "binaural", 1184, 47, 2048, spot=(3, 1100))
+
+
 def test_unsupported_shapes_fail_loudly():
     with pytest.raises(bf.BeamformError):
         bf.Beamformer(bf.make_config("mvdr", mics="circ8", hop=2048), 1)      # 8 x 4096-point spectra exceed shared memory
