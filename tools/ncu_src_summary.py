@@ -30,7 +30,11 @@ for r in rows:
     except ValueError:
         continue
     e = by_line[key]
-    num = lambda v: int(float(v)) if v not in ("", "-") else 0
+    def num(v):
+        try:
+            return int(float(v))
+        except ValueError:   # "", "-", or a source line whose inline asm broke the CSV columns
+            return 0
     e[0] += num(r[i_samp])
     e[1] += num(r[i_inst])
     e[2] += num(r[i_thr])
