@@ -26,18 +26,34 @@ def _stale():
 
 
 def build(force=False, verbose=False):
+    """Every .cu file is compiled to an object in parallel (one nvcc per file), then linked into the shared library."""
     if not force and not _stale():
         return LIB
+    from concurrent.futures import ThreadPoolExecutor
+    import tempfile
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     extra = os.environ.get("BF_NVCC_EXTRA", "").split()   # profiling builds only, e.g. -DBF_PHASE_TIMERS
     out = os.environ.get("BF_LIB_OUT", LIB)                # profiling builds: write a variant library elsewhere
-    cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", out] + [os.path.join(CSRC, s) for s in SOURCES]
-    r = subprocess.run(cmd, capture_output=True, text=True)
-    if verbose or r.returncode != 0:
-        sys.stderr.write(r.stdout + r.stderr)
-    if r.returncode != 0:
-        raise RuntimeError("nvcc failed building libbeamform_b200.so")
-    return LIB
+    cflags = [f for f in NVCC_FLAGS if f != "-shared"] + extra + (["-Xptxas", "-v"] if verbose else [])
+    with tempfile.TemporaryDirectory(prefix="bf_build_") as td:
+        def one(src):
+            obj = os.path.join(td, src.replace(".cu", ".o"))
+            r = subprocess.run([nvcc] + cflags + ["-c", "-o", obj, os.path.join(CSRC, src)], capture_output=True, text=True)
+            return src, obj, r
+        with ThreadPoolExecutor(max_workers=min(len(SOURCES), os.cpu_count() or 1)) as ex:
+            results = list(ex.map(one, SOURCES))
+        failed = [src for src, _, r in results if r.returncode != 0]
+        if verbose or failed:
+            for _, _, r in results:
+                sys.stderr.write(r.stdout + r.stderr)
+        if failed:
+            raise RuntimeError("nvcc failed building " + ", ".join(failed))
+        r = subprocess.run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", out] + [obj for _, obj, _ in results],
+                           capture_output=True, text=True)
+        if r.returncode != 0:
+            sys.stderr.write(r.stdout + r.stderr)
+            raise RuntimeError("nvcc failed linking libbeamform_b200.so")
+    return out
 
 
 if __name__ == "__main__":
