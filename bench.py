@@ -441,6 +441,21 @@ def main():
             traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic_%s.json" % args.workload))).get("dram_bytes_per_launch")
         except Exception:
             pass
+        if wl["algo"] in ("mvdr", "lcmv", "gss"):
+            # measured selection density of the workload (outside the timed region): the per-bin solves only run for the
+            # (bin, frame) items that pass the magnitude gate, so the cost of these nodes scales with it
+            try:
+                nb = min(B, 16)
+                flags = torch.zeros((nb, T, 2 * H), dtype=torch.uint8, device=dev)
+                probe = bf.Beamformer(cfg, n_streams=nb)
+                probe.set_capture(flags.data_ptr())
+                probe.process_device(x.data_ptr(), y.data_ptr(), T, stream_ptr=stream.cuda_stream, in_stream_stride=M * L, in_mic_stride=L, out_stream_stride=L)
+                torch.cuda.synchronize()
+                config["selected_items_per_frame"] = float((flags & 1)[:, :, :H + 1].float().sum().item() / (nb * T))
+                config["selected_fraction_of_half_spectrum"] = config["selected_items_per_frame"] / (H + 1)
+                del probe, flags
+            except Exception as ex:
+                config["selected_fraction_error"] = repr(ex)[:120]
         cpu = None
         if not args.no_cpu and world == 1:
             v, dt, sample = cpu_sample(cfg, wl["algo"], mic_xy, cores, 77, H, target_s=15.0)
