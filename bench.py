@@ -36,6 +36,9 @@ WORKLOADS = {
     # the mvdr kernel keeps two streams resident per SM, so a multiple of 296 leaves no partially filled last wave.
     "c2": dict(name="C2: MVDR 8-mic 1024-pt, energy-thresholded bins, batched synthetic streams", algo="mvdr", mics="circ8",
                n_streams=1184, hops_per_step=188, interferers=(), kernel="sel_pairs_kernel<mvdr>"),
+    # same workload with the gate opened 5x (freq_mag_threshold 0.0002): the selection density SURVEY.md section 8d expected (20-30 %)
+    "c2hi": dict(name="C2 variant: MVDR 8-mic 1024-pt, freq_mag_threshold 0.0002 (dense selection)", algo="mvdr", mics="circ8", n_streams=1184,
+                 hops_per_step=188, interferers=(), kernel="sel_pairs_kernel<mvdr>", params=dict(freq_mag_threshold=0.0002)),
     "c1": dict(name="C1: DAS 3-mic (aira3) 1024-pt, batched synthetic streams", algo="das", mics="aira3", n_streams=2048,
                hops_per_step=188, interferers=(), kernel="das_pairs_kernel<8>"),
     "c3l": dict(name="C3: LCMV 8-mic, 3 interferers", algo="lcmv", mics="circ8", n_streams=1184, hops_per_step=188,
@@ -293,6 +296,7 @@ def main():
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--streams", type=int, default=0, help="override streams per GPU")
     ap.add_argument("--hops", type=int, default=0, help="override hops per step")
+    ap.add_argument("--param", action="append", default=[], metavar="KEY=VALUE", help="override a node parameter of the workload (launch-file key)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
@@ -302,6 +306,9 @@ def main():
         wl["n_streams"] = args.streams
     if args.hops:
         wl["hops_per_step"] = args.hops
+    if args.param:
+        wl["params"] = dict(wl.get("params", {}), **{k: float(v) for k, v in (kv.split("=", 1) for kv in args.param)})
+        wl["name"] += " [" + ", ".join(args.param) + "]"
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -320,7 +327,7 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return 0
-        cfg = bf.make_config(wl["algo"], mics=wl["mics"], hop=H, interferers=wl["interferers"])
+        cfg = bf.make_config(wl["algo"], mics=wl["mics"], hop=H, interferers=wl["interferers"], **wl.get("params", {}))
         kind = cpu_kind(wl["algo"])
         for _ in range(max(0, min(args.warmup, 1))):
             run_cpu_reference(cfg, wl["algo"], mic_xy, cores, max(8, 24 * 512 // H), 5, cores, H)
@@ -347,7 +354,7 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    cfg = bf.make_config(wl["algo"], mics=wl["mics"], hop=H, interferers=wl["interferers"], device=local_rank)
+    cfg = bf.make_config(wl["algo"], mics=wl["mics"], hop=H, interferers=wl["interferers"], device=local_rank, **wl.get("params", {}))
     beam = bf.Beamformer(cfg, n_streams=B)
     L = T * H
     x = device_synth(torch, mic_xy, B, L, seed=0xBEA4F0 + 1000 * rank, device=dev)

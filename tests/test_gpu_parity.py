@@ -110,6 +110,21 @@ def test_mvdr_matches_oracle_and_selection_is_bit_exact(mics, theta):
     assert err <= REL_L2_TOL
 
 
+@pytest.mark.parametrize("thr", [0.000022, 0.00001])
+def test_mvdr_dense_selection_matches_oracle(thr):
+    """Gate opened far enough that a frame pair carries several hundred items (25 % / all in-band bins selected): the kernel
+    switches to its lane-pair scheme and runs more than one batch per pair."""
+    cfg = bf.make_config("mvdr", mics="circ8", freq_mag_threshold=thr)
+    x = synth_batch(bf.GEOMETRIES["circ8"], 2, 41 * H, seed=23)
+    ref, sel, _ = oracle_with_flags(cfg, x)
+    got, flags, _ = run_device(cfg, x)
+    assert sel[:, 4:, :513].mean() > 0.2
+    assert np.array_equal(flags & 1, sel), "selected-bin set must be bit-exact"
+    err = finite_rel_l2(got, ref)
+    print("mvdr dense", thr, "rel_l2", err, "selected fraction", sel[:, :, :513].mean())
+    assert err <= REL_L2_TOL
+
+
 def test_lcmv_with_interference_events_matches_oracle():
     cfg = bf.make_config("lcmv", mics="circ8", initial_angle=0.0, interferers=(80.0, -60.0, 150.0))
     x = synth_batch(bf.GEOMETRIES["circ8"], 2, 100 * H, seed=31)
