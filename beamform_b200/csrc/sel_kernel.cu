@@ -366,8 +366,28 @@ __device__ __forceinline__ float2 lcmv_finish(const KernelParams& p, const HermL
   return make_float2((float)y.x, (float)y.y);
 }
 
+// One MVDR item, out of line: ptxas allocates its registers on its own instead of across the whole frame-pair loop
+// (the kernel is capped at 128 registers for two CTAs per SM; inlined, the solve's live ranges spill into the transforms).
+template <int kDepth>
+__device__ __noinline__ float2 mvdr_item_fn(const KernelParams& p, const float2* ring_l, float2* my, int slot, const float2* steer_l) {
+  RingPipe<kDepth> pipe;
+  pipe.ring_l = ring_l;
+  pipe.my = my;
+  pipe.mic_stride = (size_t)p.Lsel;
+  pipe.slot_stride = (size_t)p.M * p.Lsel;
+  pipe.M = p.M; pipe.D = p.ring_depth;
+  pipe.slot_base = slot;
+  pipe.n_sh = p.P; pipe.sh_off = 0; pipe.extra_off = p.P; pipe.x_off = p.P; pipe.n_req = p.P + 1;
+  pipe.next_k = 0; pipe.next_stage = 0; pipe.read_stage = 0;
+  HermLower<8, float> A;
+  float invd[8];
+  float2 x[8];
+  single_cov_chol<8, float>(p, A, invd, pipe, x);
+  return mvdr_finish<8, float>(p, A, invd, x, steer_l);
+}
+
 template <int ALGO>
-__global__ void __launch_bounds__(kSelThreads, ALGO == ALGO_LCMV ? 1 : 2) sel_pairs_kernel(const KernelParams p, const int use_tma) {
+__global__ void __launch_bounds__(kSelThreads, ALGO == ALGO_LCMV ? 1 : 2) sel_pairs_kernel(const __grid_constant__ KernelParams p, const int use_tma) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   float2* tw = reinterpret_cast<float2*>(smem_raw);             // [32][32]
   float2* ztiles = tw + 1024;                                     // [8][1024] exchange tile, then Z linear
@@ -611,22 +631,10 @@ __global__ void __launch_bounds__(kSelThreads, ALGO == ALGO_LCMV ? 1 : 2) sel_pa
             const int pitch = (kDepth * M) | 1;              // odd pitch in float2: conflict-free 8-byte accesses
             if (q < n_items) {
               const int l = sc.items[q] >> 1, f = sc.items[q] & 1;
-              RingPipe<kDepth> pipe;
-              pipe.ring_l = p.hist + (size_t)s * D * M * p.Lsel + sc.sel_slot[l];
-              pipe.my = ztiles + (size_t)tid * pitch;
-              pipe.mic_stride = (size_t)p.Lsel;
-              pipe.slot_stride = (size_t)M * p.Lsel;
-              pipe.M = M; pipe.D = D;
               int slot = (fr0 + f - p.P) % D;                // ring slot of frame (t+f) - P
               if (slot < 0) slot += D;
-              pipe.slot_base = slot;
-              pipe.n_sh = p.P; pipe.sh_off = 0; pipe.extra_off = p.P; pipe.x_off = p.P; pipe.n_req = p.P + 1;
-              pipe.next_k = 0; pipe.next_stage = 0; pipe.read_stage = 0;
-              HermLower<8, float> A;
-              float invd[8];
-              float2 x[8];
-              single_cov_chol<8, float>(p, A, invd, pipe, x);
-              sc.y[f][l] = mvdr_finish<8, float>(p, A, invd, x, p.steer + (size_t)l * p.C * M);
+              sc.y[f][l] = mvdr_item_fn<kDepth>(p, p.hist + (size_t)s * D * M * p.Lsel + sc.sel_slot[l], ztiles + (size_t)tid * pitch, slot,
+                                                p.steer + (size_t)l * p.C * M);
             }
           };
           if (cap > 11 * M) run(IC<11>{});                   // P + 1 <= 11 frames at once is the common launch value (P = 10)
