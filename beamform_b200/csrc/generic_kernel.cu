@@ -1602,6 +1602,126 @@ __global__ void __launch_bounds__(kNlmsWarps * 32) gsc_nlms_kernel(const __grid_
   if (lane == 0) p.gsc_head[s] = head;
 }
 
+// Fast path of the NLMS for the launch-file shape (filter_size 128, 2-4 microphones): compile-time channel count, the
+// lane's four taps of every filter and delay line in registers between the filter output and the update, ring positions
+// computed once per sample, and the 2(M-1) sums of a sample reduced by one interleaved butterfly.  Same arithmetic per
+// element and the same state layout as gsc_nlms_kernel.
+template <int MC>
+__global__ void __launch_bounds__(kNlmsWarps * 32) gsc_nlms_fast_kernel(const __grid_constant__ KernelParams p) {
+  constexpr int F = 128, Q = 4, M = MC + 1;
+  extern __shared__ __align__(16) float nlms_smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int sl = blockIdx.x * kNlmsWarps + warp;
+  if (sl >= p.n_streams) return;
+  const int s = sl + p.stream_begin;
+  constexpr int per_warp = (MC + 1) * F + M * 32 + 32;
+  float* blk = nlms_smem + (size_t)warp * per_warp;   // [MC][F] blocking-matrix delay lines (rings)
+  float* lst = blk + MC * F;                           // [F] last outputs (ring)
+  float* tile = lst + F;                               // [M][32]
+  float* otile = tile + M * 32;                        // [32]
+  float* st = p.gsc_state + (size_t)s * (2 * MC + 1) * F;
+  for (int i = lane; i < MC * F; i += 32) blk[i] = st[i];
+  for (int i = lane; i < F; i += 32) lst[i] = st[2 * MC * F + i];
+  float flt[MC][Q];
+#pragma unroll
+  for (int i = 0; i < MC; i++)
+#pragma unroll
+    for (int q = 0; q < Q; q++) flt[i][q] = st[(MC + i) * F + lane + 32 * q];
+  int head = p.gsc_head[s];
+  __syncwarp();
+  const int nh = p.hop_end - p.hop_begin;
+  const long long n_samples = (long long)nh * p.H, mic_stride = n_samples;
+  const float* al = p.gsc_aligned + (size_t)sl * p.gsc_aligned_stream_stride;
+  float* out = p.out + (size_t)s * p.out_stream_stride + (size_t)p.hop_begin * p.H;
+  const float fM = (float)M, invF = 1.0f / (float)F;
+  const int my_ch = lane < MC ? lane : 0;
+  for (long long base = 0; base < n_samples; base += 32) {
+#pragma unroll
+    for (int i = 0; i < M; i++) tile[i * 32 + lane] = al[(size_t)i * mic_stride + base + lane];
+    __syncwarp();
+#pragma unroll 1
+    for (int jj = 0; jj < 32; jj++) {
+      float a[M];
+#pragma unroll
+      for (int i = 0; i < M; i++) a[i] = tile[i * 32 + jj];
+      float das = 0.0f;
+#pragma unroll
+      for (int i = 0; i < M; i++) das = __fadd_rn(das, a[i]);   // gsc.cpp:116-121
+      float o = __fdiv_rn(das, fM);
+      if (lane < MC) blk[lane * F + head] = __fsub_rn(tile[(lane + 1) * 32 + jj], tile[lane * 32 + jj]);   // gsc.cpp:124 (shift_data)
+      const int hd = (head + 1) & (F - 1);
+      __syncwarp();
+      float b[MC][Q], dot[MC], pw[MC];
+#pragma unroll
+      for (int i = 0; i < MC; i++) {
+        dot[i] = 0.f; pw[i] = 0.f;
+#pragma unroll
+        for (int q = 0; q < Q; q++) {
+          b[i][q] = blk[i * F + ((hd + lane + 32 * q) & (F - 1))];
+          dot[i] = fmaf(flt[i][q], b[i][q], dot[i]);
+          pw[i] = fmaf(b[i][q], b[i][q], pw[i]);
+        }
+      }
+#pragma unroll
+      for (int sh = 16; sh > 0; sh >>= 1)
+#pragma unroll
+        for (int i = 0; i < MC; i++) {
+          dot[i] += __shfl_xor_sync(0xffffffffu, dot[i], sh);
+          pw[i] += __shfl_xor_sync(0xffffffffu, pw[i], sh);
+        }
+#pragma unroll
+      for (int i = 0; i < MC; i++) o = __fsub_rn(o, dot[i]);   // out[j] -= block_out (gsc.cpp:131-134)
+      if (lane == 0) lst[head] = o;                             // gsc.cpp:138
+      __syncwarp();
+      float lp = 0.f;
+#pragma unroll
+      for (int q = 0; q < Q; q++) { const float v = lst[lane + 32 * q]; lp = fmaf(v, v, lp); }
+      lp = warp_sum(lp);
+      const float last_out_power = __fsqrt_rn(lp * invF);
+      if ((double)last_out_power < p.gsc_vad_threshold || !p.gsc_use_vad) {
+        // step sizes (gsc.cpp:147-156): lane i forms the quotients of channel i
+        float my_pw = pw[0];
+#pragma unroll
+        for (int i = 1; i < MC; i++) my_pw = (my_ch == i) ? pw[i] : my_pw;
+        const float block_power = __fsqrt_rn(my_pw * invF);
+        float my_mu;
+        if (p.gsc_mu0 * (double)block_power / (double)last_out_power < p.gsc_mu_max) my_mu = (float)(p.gsc_mu0 / (double)last_out_power);
+        else my_mu = (float)(p.gsc_mu0 / (double)block_power);
+        if (isnan(my_mu) || isinf(my_mu)) my_mu = 0.0f;
+#pragma unroll
+        for (int i = 0; i < MC; i++) {
+          const float g = __fmul_rn(__shfl_sync(0xffffffffu, my_mu, i), o);
+#pragma unroll
+          for (int q = 0; q < Q; q++) {
+            float f = __fadd_rn(flt[i][q], __fmul_rn(g, b[i][q]));   // filter[i][k] += this_mu*out[j]*block_matrix[i][k]
+            if (isnan(f)) f = 0.0f;
+            flt[i][q] = f;
+          }
+        }
+      }
+      if (lane == 0) otile[jj] = o;
+      head = hd;
+      __syncwarp();
+    }
+    out[base + lane] = otile[lane];
+    __syncwarp();
+  }
+  for (int i = lane; i < MC * F; i += 32) st[i] = blk[i];
+  for (int i = lane; i < F; i += 32) st[2 * MC * F + i] = lst[i];
+#pragma unroll
+  for (int i = 0; i < MC; i++)
+#pragma unroll
+    for (int q = 0; q < Q; q++) st[(MC + i) * F + lane + 32 * q] = flt[i][q];
+  if (lane == 0) p.gsc_head[s] = head;
+}
+
+template <int MC>
+static cudaError_t launch_nlms_fast(const KernelParams& p, cudaStream_t st) {
+  const size_t smem = sizeof(float) * kNlmsWarps * ((size_t)(MC + 1) * 128 + (size_t)(MC + 1) * 32 + 32);
+  gsc_nlms_fast_kernel<MC><<<(p.n_streams + kNlmsWarps - 1) / kNlmsWarps, kNlmsWarps * 32, smem, st>>>(p);
+  return cudaGetLastError();
+}
+
 template <int NN>
 static cudaError_t launch_gsc_n(const KernelParams& p, cudaStream_t st) {
   const size_t smem = sizeof(float2) * (size_t)p.M * NN + sizeof(float) * (size_t)p.M * (NN / 2) + 16;
@@ -1621,6 +1741,13 @@ cudaError_t launch_gsc(const KernelParams& p, cudaStream_t st) {
   }
   if (e != cudaSuccess) return e;
   const int M1 = p.M - 1;
+  if (p.gsc_F == 128 && M1 >= 1 && M1 <= 3) {   // launch-file shape: filter_size 128, 2-4 microphones
+    switch (M1) {
+      case 1: return launch_nlms_fast<1>(p, st);
+      case 2: return launch_nlms_fast<2>(p, st);
+      default: return launch_nlms_fast<3>(p, st);
+    }
+  }
   const size_t smem = sizeof(float) * kNlmsWarps * ((size_t)(2 * M1 + 1) * p.gsc_F + (size_t)p.M * 32 + 32);
   e = cudaFuncSetAttribute(gsc_nlms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
