@@ -473,6 +473,7 @@ def main():
             "vs_baseline": None, "dtype": "f32 (lcmv solves f64)" if wl["algo"] == "lcmv" else "f32", "data": "synthetic", "config": config,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
                          "traffic": traffic, "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650",
+                         "frac_of_nominal_8000_gbs": (achieved / 8000.0) if achieved else None,   # the ~8 TB/s the north_star quotes
                          "kernel": wl.get("kernel", "frames_kernel_1024<%s>" % wl["algo"]), "kernel_ms_per_launch": kern_ms / max(1, kern_n),
                          "algorithmic_bytes_per_launch": alg_bytes_per_launch},
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
