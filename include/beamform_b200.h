@@ -31,11 +31,11 @@ typedef enum bf_algo {
   BF_ALGO_PHASEMPF = 5,
   BF_ALGO_MCRA = 6,   /* stand-alone MCRA noise-reduction node (mcra.cpp:62-155): first microphone only; launch keys
                          alphaS, alphaD, alphaD2, delta, L, out_amp, out_only_noise (launch/mcra.launch) */
-  BF_ALGO_GSC = 8,    /* generalized sidelobe canceller (gsc.cpp:54-197): per-microphone frequency-domain alignment, then a
+  BF_ALGO_REF = 7,    /* rosjack_ref (jack_ref.cpp:19-60): window^2 overlap-add of the first microphone, the delay-matched
+                         reference signal of the evaluation scripts */
+  BF_ALGO_GSC = 8     /* generalized sidelobe canceller (gsc.cpp:54-197): per-microphone frequency-domain alignment, then a
                          time-domain NLMS with a power-normalised step; launch keys use_vad, vad_threshold, mu0, mu_max,
                          filter_size (launch/gsc.launch) */
-  BF_ALGO_REF = 7     /* rosjack_ref (jack_ref.cpp:19-60): window^2 overlap-add of the first microphone, the delay-matched
-                         reference signal of the evaluation scripts */
 } bf_algo;
 
 typedef enum bf_status {
