@@ -15,7 +15,7 @@ import numpy as np
 
 from . import build as _build
 
-ALGOS = {"das": 0, "mvdr": 1, "lcmv": 2, "gss": 3, "phase": 4, "phasempf": 5, "mcra": 6, "ref": 7, "gsc": 8}
+from .tables import ALGOS
 MAX_MICS = 64
 MAX_INTERF = 16
 
@@ -44,30 +44,7 @@ class BfEvent(C.Structure):
     _fields_ = [("hop_index", C.c_uint32), ("kind", C.c_int32), ("id", C.c_uint32), ("value", C.c_float)]
 
 
-# <rosparam> blocks of launch/*.launch: the only place the reference's operating values live.
-LAUNCH_PARAMS = {
-    "das": {},
-    "mvdr": dict(past_windows=10, freq_mag_threshold=0.001, freq_max=16000, freq_min=100, out_amp=1.0),
-    "lcmv": dict(past_windows=10, freq_mag_threshold=0.001, freq_max=16000, freq_min=100, out_amp=1.0, interf_angle_threshold=1.0),
-    "gss": dict(freq_mag_threshold=0.001, freq_max=16000, freq_min=100, out_amp=0.1, interf_angle_threshold=1.0, mu=0.001, **{"lambda": 0.0}),
-    "phase": dict(min_phase=10.0, min_mag=0.05, smooth_size=5),   # min_mag/smooth_size are never read by phase.cpp (B-11)
-    "phasempf": dict(min_phase=30.0, min_mag=0.05, smooth_size=3, MCRA_alphaS=0.95, MCRA_alphaD=0.95, MCRA_alphaD2=0.98,
-                     MCRA_delta=0.001, MCRA_L=50, MPF_alphaS=0.7, MPF_eta=0.3, MPF_rev_gamma=0.9, MPF_rev_delta=1.0,
-                     out_amp=2.5, noise_floor=0.001, out_only_noise=False, out_only_mcra=False),
-    "mcra": dict(alphaS=0.95, alphaD=0.95, alphaD2=0.98, delta=0.001, L=300, out_amp=3.5, out_only_noise=False),   # launch/mcra.launch
-    "ref": {},
-    "gsc": dict(use_vad=False, vad_threshold=0.1, mu0=0.0001, mu_max=0.1, filter_size=128),   # launch/gsc.launch (write_mu is a log file)
-}
-
-# beamform_config.yaml geometries (lines 15-17, 38-39) and the synthetic ones SURVEY.md §8d names
-GEOMETRIES = {
-    "aira3": [(0.000, 0.000), (0.000, -0.180), (-0.156, -0.090)],
-    "binaural": [(0.000, 0.000), (0.000, -0.342)],
-    "circ8": [(0.10 * np.cos(2 * np.pi * k / 8), 0.10 * np.sin(2 * np.pi * k / 8)) for k in range(8)],
-    "circ12": [(0.12 * np.cos(2 * np.pi * k / 12), 0.12 * np.sin(2 * np.pi * k / 12)) for k in range(12)],
-    "circ16": [(0.15 * np.cos(2 * np.pi * k / 16), 0.15 * np.sin(2 * np.pi * k / 16)) for k in range(16)],
-    "grid64": [(0.04 * (k % 8), 0.04 * (k // 8)) for k in range(64)],
-}
+from .tables import GEOMETRIES, LAUNCH_PARAMS  # noqa: F401  (pure data: launch-file blocks, geometries)
 
 _lib = None
 

@@ -27,6 +27,9 @@ struct KernelParams {
   // ---- per-stream state carried between launches / calls ----
   float* prev_hop;          // [B][M][H]  the hop before hop 0 of this call (zeros at start: util.h:275-277)
   float* tail;              // [B][H]     second half of the last synthesised frame (out_buff[0], util.h:301-302)
+  float* tail_out;          // [B][H]     where a launch leaves the new tails: == tail for kernels whose CTA owns a whole stream; a second
+                            //            buffer for das_pairs_kernel, whose warps cut streams at arbitrary pairs (reader and writer of a
+                            //            stream's tail may be different warps: the host swaps the two buffers after the segment)
   // ---- tables ----
   const float2* steer;      // [L][C][M]  weights[j](i,k): steering vectors, look direction k=0, interferers k>=1
   const float2* das_ceff;   // [M][N]     DAS only: Hermitian-ised effective weights (see capi.cu: build_das_ceff)

@@ -83,6 +83,7 @@ struct bf_handle {
   // ---- device ----
   float* d_prev_hop = nullptr;
   float* d_tail = nullptr;
+  float* d_tail2 = nullptr;   // das: second tail buffer (das_pairs_kernel reads one and writes the other, swapped per segment)
   int sm_count = 148;
   float2* d_steer = nullptr;
   float2* d_das_ceff = nullptr;
@@ -130,7 +131,8 @@ struct bf_handle {
   bool tables_dirty = true;
   bool profiling = false;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t> > prof_events;
-  std::mutex mtx;
+  std::mutex mtx;         // guards `pending` (setters may run on another thread, like the ROS callbacks)
+  std::mutex state_mtx;   // guards angle / interference_angles against the read-only getters
   std::vector<PendingEvent> pending;
 };
 
@@ -318,8 +320,6 @@ static void update_weights(bf_handle* h, bool ini) {
   h->gss_reset_pending = true;   // gss.cpp:90-93
 }
 
-static uint32_t bin_of_logical(const bf_handle* h, uint32_t l) { return l; }   // l = N/2+1 is FFT bin N/2+1 itself
-
 static int upload_tables(bf_handle* h, cudaStream_t st) {
   if (!h->tables_dirty) return BF_OK;
   const uint32_t N = h->N, M = h->M, L = h->L;
@@ -333,7 +333,7 @@ static int upload_tables(bf_handle* h, cudaStream_t st) {
   for (uint32_t l = 0; l < L; l++)
     for (int k = 0; k < h->C; k++)
       for (uint32_t i = 0; i < M; i++) {
-        cd w = W(h, bin_of_logical(h, l), i, k);
+        cd w = W(h, l, i, k)   /* logical bin N/2+1 is FFT bin N/2+1 itself */;
         steer[((size_t)l * h->C + k) * M + i] = make_float2((float)w.real(), (float)w.imag());
       }
   CUDA_TRY(cudaMemcpyAsync(h->d_steer, steer.data(), sizeof(float2) * nsteer, cudaMemcpyHostToDevice, st));
@@ -370,7 +370,7 @@ static int upload_tables(bf_handle* h, cudaStream_t st) {
   }
   std::vector<uint8_t> inband(L);
   for (uint32_t l = 0; l < L; l++) {
-    double f = std::fabs(h->freqs[bin_of_logical(h, l)]);   // mvdr.cpp:78,84
+    double f = std::fabs(h->freqs[l]);   // mvdr.cpp:78,84
     inband[l] = (f >= h->cfg.freq_min && f <= h->cfg.freq_max) ? 1 : 0;
   }
   CUDA_TRY(cudaMemcpyAsync(h->d_inband, inband.data(), L, cudaMemcpyHostToDevice, st));
@@ -402,6 +402,9 @@ extern "C" int bf_create(bf_handle** out, const bf_config* cfg, uint32_t n_strea
       return fail(BF_ERR_INVALID, "bf_create: too many microphones for this frame size (spectra must fit 227 KB of shared memory)");
   }
   if (cfg->algo < 0 || cfg->algo > 8) return fail(BF_ERR_INVALID, "bf_create: unknown algo");
+  if (cfg->hop == 512 && (cfg->algo == BF_ALGO_PHASE || cfg->algo == BF_ALGO_PHASEMPF || (cfg->algo == BF_ALGO_GSS && cfg->n_mics > 8)) &&
+      bf::frames_kernel_smem(cfg->n_mics) > 232448)
+    return fail(BF_ERR_INVALID, "bf_create: too many microphones for this node at 1024-point frames (spectra must fit 227 KB of shared memory)");
   if (cfg->algo == BF_ALGO_GSC) {
     if (cfg->filter_size < 32 || cfg->filter_size > 256 || cfg->filter_size % 32) return fail(BF_ERR_INVALID, "bf_create: gsc filter_size must be a multiple of 32 in [32, 256]");
     if (cfg->n_mics > 16) return fail(BF_ERR_INVALID, "bf_create: gsc supports at most 16 microphones");
@@ -449,6 +452,7 @@ extern "C" int bf_create(bf_handle** out, const bf_config* cfg, uint32_t n_strea
   const size_t prev_n = (size_t)h->B * h->M * h->H, tail_n = (size_t)h->B * h->H;
   bool ok = cudaMalloc(&h->d_prev_hop, sizeof(float) * prev_n) == cudaSuccess &&
             cudaMalloc(&h->d_tail, sizeof(float) * tail_n) == cudaSuccess &&
+            (cfg->algo != BF_ALGO_DAS || cudaMalloc(&h->d_tail2, sizeof(float) * tail_n) == cudaSuccess) &&
             cudaMalloc(&h->d_inband, h->L) == cudaSuccess &&
             cudaMalloc(&h->d_das_ceff, sizeof(float2) * h->M * h->N) == cudaSuccess &&
             cudaMalloc(&h->d_stage_in, sizeof(float) * h->M * h->H) == cudaSuccess &&
@@ -543,7 +547,7 @@ extern "C" void bf_destroy(bf_handle* h) {
   if (!h) return;
   cudaSetDevice(h->dev);
   if (h->own_stream) { cudaStreamSynchronize(h->own_stream); cudaStreamDestroy(h->own_stream); }
-  cudaFree(h->d_prev_hop); cudaFree(h->d_tail); cudaFree(h->d_steer); cudaFree(h->d_das_ceff); cudaFree(h->d_inband);
+  cudaFree(h->d_prev_hop); cudaFree(h->d_tail); cudaFree(h->d_tail2); cudaFree(h->d_steer); cudaFree(h->d_das_ceff); cudaFree(h->d_inband);
   cudaFree(h->d_stage_in); cudaFree(h->d_stage_out); cudaFree(h->d_io_in); cudaFree(h->d_io_out);
   if (h->st_h2d) cudaStreamDestroy(h->st_h2d);
   if (h->st_d2h) cudaStreamDestroy(h->st_d2h);
@@ -602,6 +606,11 @@ static void apply_event(bf_handle* h, int kind, uint32_t id, float value) {
   }
 }
 
+static void apply_event_locked(bf_handle* h, int kind, uint32_t id, float value) {
+  std::lock_guard<std::mutex> lk(h->state_mtx);
+  apply_event(h, kind, id, value);
+}
+
 extern "C" int bf_set_theta(bf_handle* h, float angle_deg) {
   if (!h) return fail(BF_ERR_INVALID, "null handle");
   std::lock_guard<std::mutex> lk(h->mtx);
@@ -620,17 +629,19 @@ static void drain_pending(bf_handle* h) {
     std::lock_guard<std::mutex> lk(h->mtx);
     ev.swap(h->pending);
   }
+  if (ev.empty()) return;
+  std::lock_guard<std::mutex> lk(h->state_mtx);
   for (const PendingEvent& e : ev) apply_event(h, e.kind, e.id, e.value);
 }
 extern "C" int bf_get_theta(bf_handle* h, double* a) {
   if (!h || !a) return fail(BF_ERR_INVALID, "null argument");
-  drain_pending(h);
+  std::lock_guard<std::mutex> lk(h->state_mtx);   // read-only: queued updates are applied by the processing thread at a hop boundary
   *a = h->angle;
   return BF_OK;
 }
 extern "C" int bf_get_interferences(bf_handle* h, double* angles, uint32_t cap, uint32_t* n) {
   if (!h || !n) return fail(BF_ERR_INVALID, "null argument");
-  drain_pending(h);
+  std::lock_guard<std::mutex> lk(h->state_mtx);
   *n = (uint32_t)h->interference_angles.size();
   for (uint32_t i = 0; i < *n && i < cap && angles; i++) angles[i] = h->interference_angles[i];
   return BF_OK;
@@ -658,7 +669,7 @@ static int run_segment(bf_handle* h, const float* in, size_t ss, size_t ms, floa
   p.n_streams = ns ? ns : h->B; p.stream_begin = (int)s0; p.M = h->M; p.H = h->H; p.N = h->N;
   p.hop_begin = 0; p.hop_end = (int)(h1 - h0);
   p.frame_index0 = (int)(h->frames_done & 0x7fffffff);
-  p.prev_hop = h->d_prev_hop; p.tail = h->d_tail;
+  p.prev_hop = h->d_prev_hop; p.tail = h->d_tail; p.tail_out = h->d_tail;
   p.steer = h->d_steer; p.das_ceff = h->d_das_ceff; p.inband = h->d_inband; p.C = h->C;
   // (mcra applies out_amp to the magnitudes itself, like phasempf)
   const bool amp = h->cfg.algo == BF_ALGO_MVDR || h->cfg.algo == BF_ALGO_LCMV || h->cfg.algo == BF_ALGO_GSS;
@@ -709,6 +720,7 @@ static int run_segment(bf_handle* h, const float* in, size_t ss, size_t ms, floa
     CUDA_TRY(cudaEventCreate(&ev1));
     CUDA_TRY(cudaEventRecord(ev0, st));
   }
+  bool swap_tails = false;
   static const bool force_generic = getenv("BF_GENERIC") != nullptr;   // debug: cross-check the generic kernel at N = 1024
   const bool gen_algo = h->cfg.algo == BF_ALGO_DAS || h->cfg.algo == BF_ALGO_PHASE || h->cfg.algo == BF_ALGO_PHASEMPF;
   static const bool force_sel_generic = getenv("BF_SEL_GENERIC") != nullptr;   // debug: cross-check the general gated kernel
@@ -734,7 +746,13 @@ static int run_segment(bf_handle* h, const float* in, size_t ss, size_t ms, floa
   else if (sel_algo && (h->N != 1024 || force_sel_generic || (h->M > 8 && h->cfg.algo != BF_ALGO_GSS)))
     CUDA_TRY(bf::launch_frames_kernel_sel(h->cfg.algo, p, st));
   else if (h->N != 1024 || (force_generic && gen_algo)) CUDA_TRY(bf::launch_frames_kernel_n(h->cfg.algo, p, st));
-  else if (h->cfg.algo == BF_ALGO_DAS && bf::das_pairs_supported(p)) CUDA_TRY(bf::launch_das_pairs(p, st, h->sm_count));
+  else if (h->cfg.algo == BF_ALGO_DAS && bf::das_pairs_supported(p)) {
+    // a stream's first and last pair may belong to different warps: the new tails go to the second buffer (no
+    // read-after-write inside the launch) and the buffers change roles once every stream chunk of the segment has run
+    p.tail_out = h->d_tail2;
+    CUDA_TRY(bf::launch_das_pairs(p, st, h->sm_count));
+    swap_tails = true;
+  }
   else if (bf::sel_pairs_supported(p, h->cfg.algo)) CUDA_TRY(bf::launch_sel_pairs(h->cfg.algo, p, st));
   else CUDA_TRY(bf::launch_frames_kernel_1024(h->cfg.algo, p, st));
   if (h->profiling) {
@@ -744,6 +762,7 @@ static int run_segment(bf_handle* h, const float* in, size_t ss, size_t ms, floa
   CUDA_TRY(bf::launch_save_prev_hop(p, (int)(h1 - h0) - 1, st));
   h->launches += 2;
   if (s0 + p.n_streams >= h->B) {   // the last stream chunk closes the segment
+    if (swap_tails) std::swap(h->d_tail, h->d_tail2);
     h->frames_done += h1 - h0;
     if (h->cfg.algo == BF_ALGO_PHASEMPF || h->cfg.algo == BF_ALGO_MCRA)
       for (uint32_t t = h0; t < h1; t++) {   // phasempf.cpp:162-176, mcra.cpp:100-113: window counters advance once per frame
@@ -763,7 +782,7 @@ extern "C" int bf_process_batch_device(bf_handle* h, const float* in, size_t ss,
   drain_pending(h);
   uint32_t e = 0, t = 0;
   while (t < n_hops) {
-    while (e < n_ev && ev[e].hop_index <= t) { apply_event(h, ev[e].kind, ev[e].id, ev[e].value); e++; }
+    while (e < n_ev && ev[e].hop_index <= t) { apply_event_locked(h, ev[e].kind, ev[e].id, ev[e].value); e++; }
     if (h->drop_left > 0) {
       // READY=false: the callback emits zeros and does not feed the ring buffers (lcmv.cpp:148-155)
       uint32_t nd = std::min<uint32_t>((uint32_t)h->drop_left, n_hops - t);
@@ -779,7 +798,7 @@ extern "C" int bf_process_batch_device(bf_handle* h, const float* in, size_t ss,
     if (rc != BF_OK) return rc;
     t = t1;
   }
-  while (e < n_ev) { apply_event(h, ev[e].kind, ev[e].id, ev[e].value); e++; }   // events at/after the end
+  while (e < n_ev) { apply_event_locked(h, ev[e].kind, ev[e].id, ev[e].value); e++; }   // events at/after the end
   return BF_OK;
 }
 

@@ -202,7 +202,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) das_pairs_kernel(const KernelP
           if (pp.two && write) o0[H + 32 * m2 + lane] = y0b + y1a;
           const float nt = pp.two ? y1b : y0b;
           mytail[32 * m2 + lane] = nt;
-          if (last) p.tail[(size_t)pp.s * H + 32 * m2 + lane] = nt;
+          if (last && write) p.tail_out[(size_t)pp.s * H + 32 * m2 + lane] = nt;
         });
       }
     }

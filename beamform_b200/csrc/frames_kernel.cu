@@ -209,7 +209,7 @@ __global__ void __launch_bounds__(288) frames_kernel_1024(const KernelParams p) 
 
 // Saves the last hop of the call as "previous hop" state for the next call (util.h ring buffer).
 __global__ void save_prev_hop_kernel(const KernelParams p, int last_hop) {
-  const int s = blockIdx.y + p.stream_begin, ch = blockIdx.x;
+  const int s = blockIdx.x + p.stream_begin, ch = blockIdx.y;   // streams on x: gridDim.y is limited to 65 535
   const float* src = p.in + (size_t)s * p.in_stream_stride + (size_t)ch * p.in_mic_stride + (size_t)last_hop * p.H;
   float* dst = p.prev_hop + ((size_t)s * p.M + ch) * p.H;
   for (int i = threadIdx.x; i < p.H; i += blockDim.x) dst[i] = src[i];
@@ -254,7 +254,7 @@ cudaError_t launch_frames_kernel_1024(int algo, const KernelParams& p, cudaStrea
 }
 
 cudaError_t launch_save_prev_hop(const KernelParams& p, int last_hop, cudaStream_t st) {
-  dim3 grid(p.M, p.n_streams);
+  dim3 grid(p.n_streams, p.M);
   save_prev_hop_kernel<<<grid, 128, 0, st>>>(p, last_hop);
   return cudaGetLastError();
 }

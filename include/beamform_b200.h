@@ -107,7 +107,8 @@ int bf_create(bf_handle** out, const bf_config* cfg, uint32_t n_streams);
 void bf_destroy(bf_handle* h);
 
 /* --- control: theta_roscallback (das.cpp:94-99) / interf_theta_roscallback (lcmv.cpp:258-309,
- *     gss.cpp:288-339).  Thread-safe; takes effect at the next hop boundary. -------------------- */
+ *     gss.cpp:288-339).  Thread-safe: the setters queue the message, the processing thread applies it at the
+ *     next hop boundary; the getters are read-only and report the state as of the last processed hop. ------ */
 int bf_set_theta(bf_handle* h, float angle_deg);
 int bf_set_interference(bf_handle* h, uint16_t id, float angle_deg);
 int bf_get_theta(bf_handle* h, double* angle_deg);

@@ -75,6 +75,20 @@ def from_product_config(cfg):
     return o
 
 
+def config_from_fields(fields):
+    """BfoConfig from the plain dict of beamform_b200/tables.py:plain_config_fields (no product library involved)."""
+    o = BfoConfig()
+    for name, _ in BfoConfig._fields_:
+        v = fields[name]
+        if isinstance(v, (list, tuple)):
+            arr = getattr(o, name)
+            for i, a in enumerate(v):
+                arr[i] = a
+        else:
+            setattr(o, name, v)
+    return o
+
+
 class Oracle:
     def __init__(self, cfg):
         self.cfg = cfg if isinstance(cfg, BfoConfig) else from_product_config(cfg)

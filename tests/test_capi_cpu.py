@@ -86,3 +86,22 @@ def test_create_without_device_fails_loudly():
     assert rc == 2 and not h.value, "no device must be BF_ERR_NO_DEVICE: there is no CPU fallback"
     with pytest.raises(bf.BeamformError):
         bf.Beamformer(cfg, 1)
+
+
+def test_plain_config_table_matches_bf_config_init():
+    """bench.py's reference arm builds its configuration from beamform_b200/tables.py without loading the product library:
+    the table must agree field by field with what bf_config_init + bf_config_set produce."""
+    from beamform_b200 import tables
+    from oracle_lib import BfoConfig, config_from_fields
+    cases = [("das", "aira3", {}), ("mvdr", "circ8", dict(freq_mag_threshold=0.0002)), ("lcmv", "circ8", dict(interferers=(80.0, -60.0, 150.0))),
+             ("gss", "circ8", dict(interferers=(80.0, -60.0, 150.0))), ("phase", "aira3", {}), ("phasempf", "binaural", dict(hop=2048)),
+             ("mcra", "aira3", {}), ("ref", "aira3", {}), ("gsc", "aira3", {}), ("phasempf", "aira3", dict(launch=False)), ("mcra", "aira3", dict(launch=False))]
+    for algo, mics, kw in cases:
+        prod = bf.make_config(algo, mics=mics, **kw)
+        plain = config_from_fields(tables.plain_config_fields(algo, mics=mics, **kw))
+        for name, _ in BfoConfig._fields_:
+            a, b = getattr(prod, name), getattr(plain, name)
+            if hasattr(a, "__len__"):
+                assert list(a) == list(b), (algo, name)
+            else:
+                assert a == b, (algo, name, a, b)
