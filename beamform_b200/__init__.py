@@ -70,6 +70,7 @@ def lib():
     L.bf_get_theta.argtypes = [C.c_void_p, P(C.c_double)]
     L.bf_get_interferences.argtypes = [C.c_void_p, P(C.c_double), C.c_uint32, P(C.c_uint32)]
     L.bf_process_hop.argtypes = [C.c_void_p, P(P(C.c_float)), P(C.c_float), C.c_uint32]
+    L.bf_apply_weights.argtypes = [C.c_void_p, P(P(C.c_float)), P(C.c_float), C.c_uint32]
     L.bf_process_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p, C.c_size_t, C.c_uint32,
                                    P(BfEvent), C.c_uint32]
     L.bf_process_batch_device.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p, C.c_size_t, C.c_uint32,
@@ -196,6 +197,15 @@ class Beamformer:
         ptrs = (C.POINTER(C.c_float) * self.n_mics)(*[x[m].ctypes.data_as(C.POINTER(C.c_float)) for m in range(self.n_mics)])
         out = np.empty(self.hop, dtype=np.float32)
         _check(lib().bf_process_hop(self._h, ptrs, out.ctypes.data_as(C.POINTER(C.c_float)), self.hop), "bf_process_hop")
+        return out
+
+    def apply_weights(self, frames):
+        """The weight_func seam (util.h:289): frames [M][fft_win] float32 -> fft_win windowed output samples, before overlap-add."""
+        x = np.ascontiguousarray(frames, dtype=np.float32)
+        assert x.shape == (self.n_mics, self.fft_win)
+        ptrs = (C.POINTER(C.c_float) * self.n_mics)(*[x[m].ctypes.data_as(C.POINTER(C.c_float)) for m in range(self.n_mics)])
+        out = np.empty(self.fft_win, dtype=np.float32)
+        _check(lib().bf_apply_weights(self._h, ptrs, out.ctypes.data_as(C.POINTER(C.c_float)), self.fft_win), "bf_apply_weights")
         return out
 
     def process(self, x, events=()):

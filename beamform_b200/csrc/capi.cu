@@ -30,6 +30,8 @@ bool das_pairs_supported(const KernelParams& p);
 cudaError_t launch_das_pairs(const KernelParams& p, cudaStream_t st, int sm_count);
 bool sel_pairs_supported(const KernelParams& p, int algo);
 cudaError_t launch_sel_pairs(int algo, const KernelParams& p, cudaStream_t st);
+bool sel_stream_supported(const KernelParams& p, int algo, const uint8_t* inband_host);
+cudaError_t launch_sel_stream(int algo, const KernelParams& p, cudaStream_t st);
 cudaError_t launch_frames_kernel_n(int algo, const KernelParams& p, cudaStream_t st);
 size_t frames_kernel_n_smem(int N, int M, int algo);
 cudaError_t launch_frames_kernel_sel(int algo, const KernelParams& p, cudaStream_t st);
@@ -91,6 +93,7 @@ struct bf_handle {
   int* d_gsc_head = nullptr;
   size_t gsc_aligned_cap = 0;
   uint8_t* d_inband = nullptr;
+  std::vector<uint8_t> inband_host;   // copy of the device table (kernel selection)
   uint8_t* d_capture = nullptr;
   size_t steer_cap = 0;
   int* d_sel_slot = nullptr;
@@ -130,6 +133,7 @@ struct bf_handle {
   int drop_left = 0;
   bool tables_dirty = true;
   bool profiling = false;
+  bool raw_frame_mode = false;   // bf_apply_weights: the smoother of phasempf stays with the caller (phasempf.cpp:331-334)
   std::vector<std::pair<cudaEvent_t, cudaEvent_t> > prof_events;
   std::mutex mtx;         // guards `pending` (setters may run on another thread, like the ROS callbacks)
   std::mutex state_mtx;   // guards angle / interference_angles against the read-only getters
@@ -374,6 +378,7 @@ static int upload_tables(bf_handle* h, cudaStream_t st) {
     inband[l] = (f >= h->cfg.freq_min && f <= h->cfg.freq_max) ? 1 : 0;
   }
   CUDA_TRY(cudaMemcpyAsync(h->d_inband, inband.data(), L, cudaMemcpyHostToDevice, st));
+  h->inband_host = inband;
   CUDA_TRY(cudaStreamSynchronize(st));   // host vectors go out of scope
   h->tables_dirty = false;
   return BF_OK;
@@ -699,7 +704,7 @@ static int run_segment(bf_handle* h, const float* in, size_t ss, size_t ms, floa
   p.thr_phase_mag = (float)(h->cfg.mag_threshold * (double)h->M * (double)h->N);
   p.mag_mult = (float)h->cfg.mag_mult;
   p.min_mag = (float)h->cfg.min_mag;
-  p.mpf_state = h->d_mpf_state; p.smooth_hist = h->d_smooth_hist; p.smooth_size = h->cfg.smooth_size;
+  p.mpf_state = h->d_mpf_state; p.smooth_hist = h->d_smooth_hist; p.smooth_size = h->raw_frame_mode ? 1 : h->cfg.smooth_size;
   p.mcra_alphaS = (float)h->cfg.MCRA_alphaS; p.mcra_alphaD = (float)h->cfg.MCRA_alphaD;
   p.mcra_alphaD2 = (float)h->cfg.MCRA_alphaD2; p.mcra_delta = (float)h->cfg.MCRA_delta;
   p.mcra_L = h->cfg.MCRA_L; p.mcra_cur_L0 = h->mcra_cur_L; p.mcra_first0 = h->mcra_first;
@@ -753,6 +758,7 @@ static int run_segment(bf_handle* h, const float* in, size_t ss, size_t ms, floa
     CUDA_TRY(bf::launch_das_pairs(p, st, h->sm_count));
     swap_tails = true;
   }
+  else if (bf::sel_stream_supported(p, h->cfg.algo, h->inband_host.data())) CUDA_TRY(bf::launch_sel_stream(h->cfg.algo, p, st));
   else if (bf::sel_pairs_supported(p, h->cfg.algo)) CUDA_TRY(bf::launch_sel_pairs(h->cfg.algo, p, st));
   else CUDA_TRY(bf::launch_frames_kernel_1024(h->cfg.algo, p, st));
   if (h->profiling) {
@@ -885,6 +891,34 @@ extern "C" int bf_process_hop(bf_handle* h, const float* const* in, float* out, 
   CUDA_TRY(cudaMemcpyAsync(h->h_stage_out, h->d_stage_out, sizeof(float) * h->H, cudaMemcpyDeviceToHost, st));
   CUDA_TRY(cudaStreamSynchronize(st));
   memcpy(out, h->h_stage_out, sizeof(float) * h->H);
+  return BF_OK;
+}
+
+// The per-frame operator seam: void (*weight_func)(jack_ringbuffer_t **in, rosjack_data *out) of util.h:289 — one frame
+// of fft_win samples per microphone in, fft_win windowed output samples out (util.h:244-253), before the overlap-add.
+// The fused kernels overlap-add internally, so the frame [a | b] is run as "previous hop a, hop b" from an empty
+// overlap-add tail: the first half of the synthesised frame is the hop's output, the second half is the new tail.
+extern "C" int bf_apply_weights(bf_handle* h, const float* const* in_frames, float* out_frame, uint32_t fft_win) {
+  if (!h || !in_frames || !out_frame) return fail(BF_ERR_INVALID, "bf_apply_weights: null argument");
+  if (h->B != 1) return fail(BF_ERR_INVALID, "bf_apply_weights: handle must have n_streams == 1");
+  if (fft_win != h->N) return fail(BF_ERR_INVALID, "bf_apply_weights: frame length != fft_win (2 * JACK period)");
+  if (h->cfg.algo == BF_ALGO_GSC || h->cfg.algo == BF_ALGO_REF)
+    return fail(BF_ERR_INVALID, "bf_apply_weights: gsc and rosjack_ref have no per-frame operator of this shape (do_overlap_bymic / window only)");
+  CUDA_TRY(cudaSetDevice(h->dev));
+  cudaStream_t st = h->own_stream;
+  const uint32_t H = h->H;
+  for (uint32_t m = 0; m < h->M; m++) {
+    CUDA_TRY(cudaMemcpyAsync(h->d_prev_hop + (size_t)m * H, in_frames[m], sizeof(float) * H, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(h->d_stage_in + (size_t)m * H, in_frames[m] + H, sizeof(float) * H, cudaMemcpyHostToDevice, st));
+  }
+  CUDA_TRY(cudaMemsetAsync(h->d_tail, 0, sizeof(float) * H, st));
+  h->raw_frame_mode = true;
+  int rc = bf_process_batch_device(h, h->d_stage_in, (size_t)h->M * H, H, h->d_stage_out, H, 1, nullptr, 0, st);
+  h->raw_frame_mode = false;
+  if (rc != BF_OK) return rc;
+  CUDA_TRY(cudaMemcpyAsync(out_frame, h->d_stage_out, sizeof(float) * H, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaMemcpyAsync(out_frame + H, h->d_tail, sizeof(float) * H, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
   return BF_OK;
 }
 

@@ -120,6 +120,14 @@ int bf_get_interferences(bf_handle* h, double* angles, uint32_t cap, uint32_t* n
  *     One hop in, one hop out, one hop of latency; requires n_streams == 1. --------------------- */
 int bf_process_hop(bf_handle* h, const float* const* in, float* out, uint32_t nframes);
 
+/* --- the per-frame operator seam: `void (*weight_func)(jack_ringbuffer_t **in, rosjack_data *out)` handed to
+ *     do_overlap (util.h:289-314), i.e. apply_weights of every node (das.cpp:47-70, mvdr.cpp:62-115, ...).
+ *     `in_frames[m]` = the fft_win samples of microphone m the ring buffer holds ([previous hop | new hop]),
+ *     `out_frame` = fft_win windowed output samples (util.h:244-253); the caller overlap-adds (and, for phasempf,
+ *     smooths: phasempf.cpp:331-334).  Advances the node's per-frame state (histories, W, MCRA) by one frame.
+ *     n_streams == 1; not for gsc / rosjack_ref; do not mix with bf_process_* on one handle. ------------------- */
+int bf_apply_weights(bf_handle* h, const float* const* in_frames, float* out_frame, uint32_t fft_win);
+
 /* --- offline batched driver: the same callback applied to n_hops consecutive hops of n_streams
  *     independent streams.  Host variant copies H2D/D2H itself; the device variant takes device
  *     pointers and a CUDA stream (cudaStream_t as void*).  Layout: in[s*in_stream_stride +

@@ -39,9 +39,10 @@ def build():
         subprocess.run(["make", "-C", os.path.join(ROOT, "oracle"), "-s", "-f", "Makefile.ref"], check=True)
 
 
-def run_ref(algo, cfg, x, events=(), want_interf=False):
+def run_ref(algo, cfg, x, events=(), want_interf=False, binary=None):
     """cfg: beamform_b200.BfConfig (or the oracle's BfoConfig) — every field the node reads is passed as a rosparam.
-    x: [M][L] float32.  Returns out [L] float32 (and the final interference list)."""
+    x: [M][L] float32.  Returns out [L] float32 (and the final interference list).  `binary`: run this executable instead
+    of oracle/_ref/<node>_ref (the drop-in nodes of examples/ speak the same offline ROS/JACK stand-in)."""
     x = np.ascontiguousarray(x[:1] if algo == "ref" else x, dtype=np.float32)   # rosjack_ref opens one JACK input (jack_ref.cpp:65)
     M, L = x.shape
     with tempfile.TemporaryDirectory() as td:
@@ -70,7 +71,20 @@ def run_ref(algo, cfg, x, events=(), want_interf=False):
         env = dict(os.environ, BFREF_PARAMS=pf, BFREF_IN=inf, BFREF_OUT=outf, BFREF_EVENTS=evf, BFREF_INTERF_OUT=itf,
                    BFREF_HOP=str(int(cfg.hop)), BFREF_SR=str(int(cfg.sample_rate)))
         env.pop("BFREF_VERBOSE", None)
-        subprocess.run([os.path.join(REF_DIR, BINARY.get(algo, algo + "_ref"))], env=env, check=True, stdout=subprocess.DEVNULL)
+        subprocess.run([binary or os.path.join(REF_DIR, BINARY.get(algo, algo + "_ref"))], env=env, check=True, stdout=subprocess.DEVNULL)
         out = np.fromfile(outf, dtype=np.float32)
         interf = [float(s) for s in open(itf).read().split()] if os.path.exists(itf) else []
     return (out, interf) if want_interf else out
+
+
+EXAMPLE_DIR = os.path.join(ROOT, "examples", "_bin")
+
+
+def example_available(name):
+    return os.path.exists(os.path.join(EXAMPLE_DIR, name))
+
+
+def build_examples():
+    """The drop-in nodes of examples/ need the reference's rosjack.h / util.h: built where /root/reference exists."""
+    if os.path.isdir("/root/reference/beamform/src"):
+        subprocess.run(["make", "-C", os.path.join(ROOT, "examples"), "-s"], check=True)

@@ -520,3 +520,35 @@ def test_srp_maps_match_oracle(mics, n_dirs, n_hops):
         peak = thetas[int(np.argmax(ref[0, n_hops - 1]))]
         assert abs(((peak - 25.0 + 180) % 360) - 180) <= 6.0
         assert int(np.argmax(got[0, n_hops - 1])) == int(np.argmax(ref[0, n_hops - 1]))
+
+
+# ---------------------------------------------------------------------------------------------
+# the drop-in from C++: examples/<node>_b200.cpp = the reference's node with rosjack.h / util.h unchanged (handle_params,
+# rosjack_create, ros::spin) and the DSP behind the C ABI, driven hop by hop by the offline ROS/JACK stand-in
+# ---------------------------------------------------------------------------------------------
+import ref_lib as _ref_lib
+
+_NODE_OF = {"ref": "jack_ref"}
+
+
+@pytest.mark.parametrize("name", sorted(GOLDEN_CASES))
+@pytest.mark.parametrize("seam", [False, True])
+def test_cpp_drop_in_nodes_match_reference_golden(name, seam):
+    """jack_callback -> bf_process_hop (das.cpp:72-92), theta_roscallback -> bf_set_theta (das.cpp:94-99),
+    interf_theta_roscallback -> bf_set_interference (lcmv.cpp:258-309); with seam=True the binding sits at the per-frame
+    operator instead: util.h's own do_overlap calls bf_apply_weights as its weight_func (util.h:289)."""
+    cfg, x, events = golden_build_case(name)
+    algo = GOLDEN_CASES[name]["algo"]
+    exe = "%s_b200%s" % (_NODE_OF.get(algo, algo), "_seam" if seam else "")
+    if seam and algo not in ("das", "mvdr", "lcmv", "gss", "phasempf"):
+        pytest.skip("no per-frame operator seam for this node")
+    if not _ref_lib.example_available(exe):
+        pytest.skip("examples/_bin/%s was not built (needs the reference's rosjack.h / util.h at build time)" % exe)
+    got, interf = _ref_lib.run_ref(algo, cfg, x, events=events, want_interf=True, binary=_os.path.join(_ref_lib.EXAMPLE_DIR, exe))
+    ref = _GOLD[name + "/out"]
+    assert got.shape == ref.shape
+    err = finite_rel_l2(got, ref)
+    print(exe, name, "rel_l2 vs reference", err)
+    assert err <= REL_L2_TOL
+    if algo in ("lcmv", "gss"):
+        assert interf == list(_GOLD[name + "/interf"]), "interference list must be bit-exact"
