@@ -1,4 +1,4 @@
-// Pipelined kernel for the covariance nodes (mvdr / lcmv), 1024-point frames, M <= 8, P <= 10, sm_100a.
+// Pipelined kernel for mvdr (the covariance node of BASELINE config C2), 1024-point frames, M <= 8, P <= 10, sm_100a.
 //
 //   reference path replaced (citations /root/reference/beamform/src/): util.h:217-253,289-314 (window, framing,
 //   OLA) and apply_weights of mvdr.cpp:62-115, lcmv.cpp:88-140 (history matrices past_ffts of mvdr.cpp:228-243).
@@ -32,8 +32,11 @@
 namespace bf {
 
 constexpr int kSsMicWarps = 8;
-constexpr int kSsSolvers = 7;                            // solver warps == staging batches in flight (warp w owns batch slot w)
-constexpr int kSsThreads = 512;
+// solver warps == staging batches in flight (warp w owns batch slot w): 16 warps x 128 registers.  (lcmv solves in FP64: measured on
+// B200 it is slower here than in sel_pairs_kernel -- 104 k audio-s/s with 7 solvers at 128 registers (spills), 86 k with 3 solvers at 168
+// registers, against 123 k -- so capi.cu keeps lcmv on sel_pairs_kernel; the template stays generic.)
+template <int ALGO> struct SsCfg { static constexpr int kSolvers = 7; static constexpr int kThreads = (kSsMicWarps + kSolvers + 1) * 32; };
+constexpr int kSsMaxSolvers = 7;
 constexpr int kSsBlocks = 11;                            // 32-bin blocks with on-chip history: logical bins 0..351
 constexpr int kSsBins = kSsBlocks * 32;
 constexpr int kSsSlots = 11;                             // ring slots per bin in tensor memory (P + 1 <= 11)
@@ -42,6 +45,7 @@ constexpr int kSsItems = 16;                             // bins per solver batc
 constexpr int kSsEntries = kSsSlots + 1;                 // staged per item: the 11 ring slots + X_{t+1}
 constexpr int kSsItemF2 = kSsEntries * 8 + 2;            // 98 float2 = 784 B: 16-byte multiple, odd multiple of 16 B (LDS.128 conflict-free)
 constexpr int kSsKY = 3;                                 // output-spectrum buffers in flight
+constexpr int kSsYDoneCount = kSsBins / kSsItems + 1;    // arrivals that complete y_done: every batch of the pair (<= 22) + microphone warp 0 with the remainder
 
 struct SsBatch {
   float2 item[kSsItems][kSsItemF2];   // [item][entry*8 + mic]
@@ -52,37 +56,40 @@ struct SsBatch {
 
 struct SsShared {
   float2 tw[1024];
-  float2 tile[kSsMicWarps][1024];     // per microphone warp: TMA landing zone, then FFT exchange tile
-  float2 itile[1024];                 // exchange tile of the inverse warp
-  float mags[2][8][kSsBins];
+  float2 tile[kSsMicWarps + 1][1024]; // per microphone warp: TMA landing zone, then FFT exchange tile; [8]: the inverse warp's exchange tile
+  float mags[8][2][kSsBins];          // |X_m[l]| of both frames; after the gate microphone m parks X_{t+1} in its own rows (352 float2)
+  float ygain[kSsBins];               // default output = ygain * X_0: 0.01 inside the band (mvdr.cpp:96), 1 for mvdr's bin 0, else 0
+  float tail[512];                    // overlap-add tail (inverse warp only)
   float2 y[kSsKY][2][kL1K];
-  SsBatch batch[kSsSolvers];
+  SsBatch batch[kSsMaxSolvers];
   float sqrtE[2][8];
   unsigned masks[2][kSsBlocks + 1];
-  int nbatches[kSsKY], done_cnt[kSsKY], nonfinite[kSsKY][2];
+  int nonfinite[kSsKY][2];
   int total_batches;
   short sel_slot[kSsBins];
   unsigned char inband[kSsBins];
-  uint64_t tma_bar[kSsMicWarps], full[kSsSolvers], empty[kSsSolvers], y_done[kSsKY], y_free[kSsKY];
+  uint64_t tma_bar[kSsMicWarps], empty[kSsMaxSolvers], y_done[kSsKY], y_free[kSsKY];
   uint32_t tmem_slot;
 };
 
-__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+// try_wait with a suspend-time hint: the warp is parked by the hardware until the phase completes or `ns` nanoseconds have
+// passed (no polling instructions in between: an idle solver must not eat the issue slots of the working warps)
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity, uint32_t ns = 2000u) {
   uint32_t ok;
   asm volatile(
       "{\n"
       ".reg .pred p;\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
       "selp.u32 %0, 1, 0, p;\n"
       "}\n"
       : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(ns)
       : "memory");
   return ok != 0;
 }
 // every wait of this kernel is bounded: a protocol error traps (the launch fails) instead of hanging the GPU
 __device__ __forceinline__ void ss_watchdog(unsigned& spins, long long& t0) {
-  if ((++spins & 1023u) == 0) {
+  if ((++spins & 255u) == 0) {
     const long long now = clock64();
     if (t0 == 0) t0 = now;
     else if (now - t0 > (1ll << 35)) __trap();   // ~17 s at 1.9 GHz without progress
@@ -94,6 +101,18 @@ __device__ __forceinline__ void ss_wait(uint64_t* bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) ss_watchdog(spins, t0);
 }
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory"); }
+__device__ __forceinline__ void mbar_arrive_cnt(uint64_t* bar, uint32_t cnt) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(cnt) : "memory");
+}
+// Solver wake-up goes through hardware named barriers (a blocked warp issues nothing, unlike an mbarrier poll loop): the
+// eight microphone warps bar.arrive on barrier 3 + slot once the batch in that slot is complete, the slot's solver bar.syncs.
+constexpr int kSsBarBase = 3, kSsBarThreads = (kSsMicWarps + 1) * 32;
+__device__ __forceinline__ void ss_publish(int slot) {
+  __syncwarp();
+  // bar.arrive orders this thread's earlier shared-memory writes before the barrier completes (no MEMBAR needed: it cost
+  // ~110 cycles per call on the microphone warps' critical path)
+  asm volatile("bar.arrive %0, %1;" ::"r"(kSsBarBase + slot), "r"(kSsBarThreads) : "memory");
+}
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 
 __device__ __forceinline__ void tmem_st2(uint32_t taddr, float a, float b) {
@@ -171,31 +190,35 @@ __device__ __noinline__ void ss_solve_batch(const KernelParams& p, SsShared& sh,
   int sg = sx + 2 + (f ? n_half : 0);
   if (sg >= Dt) sg -= Dt;
   if (sg >= Dt) sg -= Dt;
+  const int sold = (sx + 1 == Dt) ? 0 : sx + 1;
 #pragma unroll 1
-  for (int j = 0; j < n_half; j++) {
-    if (f == 0 || n_half + j < n_sh) {
+  for (int j = 0; j <= n_half; j++) {   // n_half shared frames per lane, then (after the butterfly) the one frame only this lane's history holds
+    bool go;
+    int e;
+    if (j < n_half) {
+      go = f == 0 || n_half + j < n_sh;
+      e = sg;
+      if (++sg == Dt) sg = 0;
+    } else {
+      __syncwarp();
+#pragma unroll
+      for (int k = 0; k < 8; k++) A.dg[k] += __shfl_xor_sync(0xffffffffu, A.dg[k], 16);
+#pragma unroll
+      for (int k = 0; k < 28; k++) {
+        A.lo[k].x += __shfl_xor_sync(0xffffffffu, A.lo[k].x, 16);
+        A.lo[k].y += __shfl_xor_sync(0xffffffffu, A.lo[k].y, 16);
+      }
+      go = sel;
+      e = f ? sx : sold;   // X_t for frame t+1, X_{t-P} for frame t
+    }
+    if (go) {
       float2 hf[8];
-      load_entry(sg, hf);
+      load_entry(e, hf);
       cov_rank1<8, T>(A, hf);
     }
-    if (++sg == Dt) sg = 0;
-  }
-  __syncwarp();
-#pragma unroll
-  for (int k = 0; k < 8; k++) A.dg[k] += __shfl_xor_sync(0xffffffffu, A.dg[k], 16);
-#pragma unroll
-  for (int k = 0; k < 28; k++) {
-    A.lo[k].x += __shfl_xor_sync(0xffffffffu, A.lo[k].x, 16);
-    A.lo[k].y += __shfl_xor_sync(0xffffffffu, A.lo[k].y, 16);
   }
   if (sel) {
     float2 x[8];
-    {
-      float2 hf[8];
-      const int sold = (sx + 1 == Dt) ? 0 : sx + 1;
-      load_entry(f ? sx : sold, hf);     // the one frame only this lane's history holds: X_t for frame t+1, X_{t-P} for frame t
-      cov_rank1<8, T>(A, hf);
-    }
     load_entry(f ? kSsSlots : sx, x);    // this lane's own frame
     T invd[8];
     chol_in_place<8, T>(p, A, invd);
@@ -207,7 +230,8 @@ __device__ __noinline__ void ss_solve_batch(const KernelParams& p, SsShared& sh,
 }
 
 template <int ALGO>
-__global__ void __launch_bounds__(kSsThreads, 1) sel_stream_kernel(const __grid_constant__ KernelParams p, const int use_tma) {
+__global__ void __launch_bounds__(SsCfg<ALGO>::kThreads, 1) sel_stream_kernel(const __grid_constant__ KernelParams p, const int use_tma) {
+  constexpr int kSsSolvers = SsCfg<ALGO>::kSolvers, kSsThreads = SsCfg<ALGO>::kThreads;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   SsShared& sh = *reinterpret_cast<SsShared*>(smem_raw);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -224,14 +248,20 @@ __global__ void __launch_bounds__(kSsThreads, 1) sel_stream_kernel(const __grid_
     sincospif(-2.0f * (float)((k1 * l) & 1023) / 1024.0f, &sn, &cs);
     sh.tw[i] = make_float2(cs, sn);
   }
-  for (int i = tid; i < kSsBins; i += kSsThreads) { sh.sel_slot[i] = (short)p.sel_slot[i]; sh.inband[i] = p.inband[i]; }
+  for (int i = tid; i < kSsBins; i += kSsThreads) {
+    const bool inb = p.inband[i] != 0 && !(ALGO == ALGO_MVDR && i == 0);
+    sh.sel_slot[i] = (short)p.sel_slot[i];
+    sh.inband[i] = inb ? 1 : 0;
+    sh.ygain[i] = inb ? 0.01f : ((ALGO == ALGO_MVDR && i == 0) ? 1.0f : 0.0f);
+  }
+  for (int i = tid; i < H; i += kSsThreads) sh.tail[i] = p.tail[(size_t)s * H + i];
   for (int i = tid; i < kSsKY * 2 * kL1K; i += kSsThreads) (&sh.y[0][0][0])[i] = make_float2(0.f, 0.f);   // bins outside the band stay 0 (mvdr.cpp:103)
-  if (tid < kSsKY) { sh.nbatches[tid] = 0; sh.done_cnt[tid] = 0; sh.nonfinite[tid][0] = 0; sh.nonfinite[tid][1] = 0; }
+  if (tid < kSsKY) { sh.nonfinite[tid][0] = 0; sh.nonfinite[tid][1] = 0; }
   if (tid == 0) {
     sh.total_batches = -1;
     for (int i = 0; i < kSsMicWarps; i++) mbar_init(&sh.tma_bar[i], 1);
-    for (int i = 0; i < kSsSolvers; i++) { mbar_init(&sh.full[i], kSsMicWarps); mbar_init(&sh.empty[i], 1); }
-    for (int i = 0; i < kSsKY; i++) { mbar_init(&sh.y_done[i], 1); mbar_init(&sh.y_free[i], 1); }
+    for (int i = 0; i < kSsSolvers; i++) mbar_init(&sh.empty[i], 1);
+    for (int i = 0; i < kSsKY; i++) { mbar_init(&sh.y_done[i], kSsYDoneCount); mbar_init(&sh.y_free[i], 1); }
   }
   mbar_fence_init();
   if (warp == 0) {
@@ -243,18 +273,23 @@ __global__ void __launch_bounds__(kSsThreads, 1) sel_stream_kernel(const __grid_
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = sh.tmem_slot;
 
-  if (warp < kSsMicWarps) {
-    // ================================================================== microphone warps
-    const int m = warp;
-    const bool have = m < M;
-    const uint32_t tm = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((warp >> 2) * kSsHalfCols);
-    float2* tile = sh.tile[m];
+  const bool is_mic = warp < kSsMicWarps, is_inv = warp == kSsMicWarps + kSsSolvers;
+  if (is_mic || is_inv) {
+    // ================================================================== transform warps: 8 microphones + the inverse warp.
+    // They share ONE copy of the FFT code (IFFT(G) = swap(FFT(swap(G)))): the instruction caches hold the hot loops of
+    // three roles at once, and a second inlined transform is 9 KB of them.
+    const int m = is_mic ? warp : 0;
+    const bool have = is_mic && m < M;
+    const uint32_t tm = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(((warp >> 2) & 1) * kSsHalfCols);
+    float2* tile = sh.tile[is_mic ? warp : kSsMicWarps];
     float* stage = reinterpret_cast<float*>(tile);
+    float2* xpark = reinterpret_cast<float2*>(&sh.mags[m][0][0]);   // X_{t+1} of this microphone between the gate and the staging
     const float* in_s = p.in + (size_t)s * p.in_stream_stride + (size_t)m * p.in_mic_stride;
-    const float2* hist_s = p.hist + (size_t)s * D * M * p.Lsel + (size_t)m * p.Lsel;   // + slot*M*Lsel + sel_slot[l]
+    float2* hist_s = p.hist + (size_t)s * D * M * p.Lsel + (size_t)m * p.Lsel;   // + slot*M*Lsel + sel_slot[l]
     double sd, cd;
     sincospi((double)lane / 1024.0, &sd, &cd);
-    const float s_l = (float)(0.5 * sd), c_l = (float)(0.5 * cd);   // analysis window * 0.5
+    // analysis window * 0.5 (microphones) / synthesis window * out_amp / N (inverse)
+    const float s_w = is_mic ? (float)(0.5 * sd) : (float)(sd * p.out_scale), c_w = is_mic ? (float)(0.5 * cd) : (float)(cd * p.out_scale);
 
     auto issue = [&](int t) {   // hops t-1..t+1 of this microphone -> tile (hop -1 = per-stream state, util.h:275-277)
       const bool two = t + 1 < p.hop_end;
@@ -266,68 +301,107 @@ __global__ void __launch_bounds__(kSsThreads, 1) sel_stream_kernel(const __grid_
     };
     if (have && use_tma && npairs > 0 && lane == 0) issue(p.hop_begin);
 
-    // ---- history of the previous calls: global ring (slot = frame % D) -> tensor memory (slot = frame % Dt) ----
+    if (is_mic) {
+      // ---- history of the previous calls: global ring (slot = frame % D) -> tensor memory (slot = frame % Dt) ----
 #pragma unroll 1
-    for (int j = 1; j <= p.P; j++) {
-      int g = p.ring_slot0 - j;
-      if (g < 0) g += D;
-      int sg = sig0 - j;
-      if (sg < 0) sg += Dt;
-      const float2* src = hist_s + (size_t)g * M * p.Lsel;
-      float2 hv[kSsBlocks];
+      for (int j = 1; j <= p.P; j++) {
+        int g = p.ring_slot0 - j;
+        if (g < 0) g += D;
+        int sg = sig0 - j;
+        if (sg < 0) sg += Dt;
+        const float2* src = hist_s + (size_t)g * M * p.Lsel;
+        float2 hv[kSsBlocks];
 #pragma unroll
-      for (int k2 = 0; k2 < kSsBlocks; k2++) {
-        const int ss = sh.sel_slot[k2 * 32 + lane];
-        hv[k2] = (have && ss >= 0) ? src[ss] : make_float2(0.f, 0.f);
+        for (int k2 = 0; k2 < kSsBlocks; k2++) {
+          const int ss = sh.sel_slot[k2 * 32 + lane];
+          hv[k2] = (have && ss >= 0) ? src[ss] : make_float2(0.f, 0.f);
+        }
+#pragma unroll
+        for (int k2 = 0; k2 < kSsBlocks; k2++) tmem_st2(tm + (uint32_t)((k2 * kSsSlots + sg) * 2), hv[k2].x, hv[k2].y);
       }
-#pragma unroll
-      for (int k2 = 0; k2 < kSsBlocks; k2++) tmem_st2(tm + (uint32_t)((k2 * kSsSlots + sg) * 2), hv[k2].x, hv[k2].y);
+      tmem_wait_st();
     }
-    tmem_wait_st();
 
     int seq0 = 0;   // staging batches published so far (identical in every microphone warp)
+#pragma unroll 1
     for (int ip = 0; ip < npairs; ip++) {
       const int t = p.hop_begin + 2 * ip;
       const bool two = t + 1 < p.hop_end;
       const int ky = ip % kSsKY;
-      int sx = sig0 + 2 * ip;
-      sx %= Dt;                                     // ring slot of frame t
-      const int sx1 = (sx + 1 == Dt) ? 0 : sx + 1;  // ring slot of frame t+1 (it still holds frame t-P)
-      // ---------------------------------------------------------------- window + forward transform
       float2 v[32];
-      if (have) {
-        if (use_tma) {
-          ss_wait(&sh.tma_bar[m], ip & 1);
-        } else {   // unaligned caller buffers: plain warp copy, no prefetch
-          const float* prev = (t - 1 < 0) ? p.prev_hop + ((size_t)s * M + m) * H : in_s + (size_t)(t - 1) * H;
-          for (int i = lane; i < H; i += 32) {
-            stage[i] = prev[i];
-            stage[H + i] = in_s[(size_t)t * H + i];
-            stage[2 * H + i] = two ? in_s[(size_t)(t + 1) * H + i] : 0.f;
+      float e0 = 0.f, e1 = 0.f;
+      bool z0 = false, z1 = false;
+      if (is_mic) {
+        // ---------------------------------------------------------------- hops -> windowed packed frame pair
+        if (have) {
+          if (use_tma) {
+            ss_wait(&sh.tma_bar[m], ip & 1);
+          } else {   // unaligned caller buffers: plain warp copy, no prefetch
+            const float* prev = (t - 1 < 0) ? p.prev_hop + ((size_t)s * M + m) * H : in_s + (size_t)(t - 1) * H;
+            for (int i = lane; i < H; i += 32) {
+              stage[i] = prev[i];
+              stage[H + i] = in_s[(size_t)t * H + i];
+              stage[2 * H + i] = two ? in_s[(size_t)(t + 1) * H + i] : 0.f;
+            }
+            __syncwarp();
           }
-          __syncwarp();
-        }
-        static_for<0, 16>([&](auto r) {
-          const float a = stage[32 * r + lane], bb = stage[512 + 32 * r + lane];
-          const float c = two ? stage[1024 + 32 * r + lane] : 0.0f;
-          const float w0 = win1024<r>(s_l, c_l);
-          const float w1 = win1024<r + 16>(s_l, c_l);
-          v[brev5(r)] = make_float2(a * w0, bb * w0);
-          v[brev5(r + 16)] = make_float2(bb * w1, c * w1);
-        });
-      } else {
+          static_for<0, 16>([&](auto r) {
+            const float a = stage[32 * r + lane], bb = stage[512 + 32 * r + lane];
+            const float c = two ? stage[1024 + 32 * r + lane] : 0.0f;
+            const float w0 = win1024<r>(s_w, c_w);
+            const float w1 = win1024<r + 16>(s_w, c_w);
+            v[brev5(r)] = make_float2(a * w0, bb * w0);
+            v[brev5(r + 16)] = make_float2(bb * w1, c * w1);
+          });
+        } else {
 #pragma unroll
-        for (int r = 0; r < 32; r++) v[r] = make_float2(0.f, 0.f);
-      }
-      __syncwarp();   // staged samples consumed: the tile becomes the exchange buffer
-      {   // sqrt of the windowed frame energies: scale of the FP32 FFT's absolute error (gate guard band)
-        float e0 = 0.f, e1 = 0.f;
+          for (int r = 0; r < 32; r++) v[r] = make_float2(0.f, 0.f);
+        }
+        __syncwarp();   // staged samples consumed: the tile becomes the exchange buffer
+        // sqrt of the windowed frame energies: scale of the FP32 FFT's absolute error (gate guard band)
 #pragma unroll
         for (int r = 0; r < 32; r++) { e0 = fmaf(v[r].x, v[r].x, e0); e1 = fmaf(v[r].y, v[r].y, e1); }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) { e0 += __shfl_xor_sync(0xffffffffu, e0, o); e1 += __shfl_xor_sync(0xffffffffu, e1, o); }
         if (lane == 0) { sh.sqrtE[0][m] = 2.0f * sqrtf(e0); sh.sqrtE[1][m] = 2.0f * sqrtf(e1); }
+      } else {
+        // ---------------------------------------------------------------- output spectra of the pair -> G = Yh_t + i Yh_{t+1}
+        ss_wait(&sh.y_done[ky], (uint32_t)(ip / kSsKY) & 1u);   // defaults written and every batch of the pair solved
+        // one inf/NaN bin makes the reference's whole inverse frame NaN; the two frames of a pair share one complex transform
+        // here, so a poisoned frame is left out of G and re-poisoned at the output without touching its partner
+        z0 = *reinterpret_cast<volatile int*>(&sh.nonfinite[ky][0]) != 0;
+        z1 = *reinterpret_cast<volatile int*>(&sh.nonfinite[ky][1]) != 0;
+        if (z0 || z1 || !two) {   // rare: drop the frame from the shared transform (every in-band bin is rewritten for the next pair anyway)
+          for (int l = lane; l < kL1K; l += 32) {
+            if (z0) sh.y[ky][0][l] = make_float2(0.f, 0.f);
+            if (z1 || !two) sh.y[ky][1][l] = make_float2(0.f, 0.f);
+          }
+          __syncwarp();
+        }
+        static_for<0, 32>([&](auto n1c) {
+          constexpr int n1 = decltype(n1c)::value;
+          const int j = n1 * 32 + lane;
+          const bool mir = (n1 > 16) || (n1 == 16 && lane != 0);   // bins above N/2: conjugate of bin N - j
+          const int l = mir ? 1024 - j : j;
+          float2 y0 = sh.y[ky][0][l], y1 = sh.y[ky][1][l];
+          if constexpr (n1 == 0 || n1 == 16) {
+            if (lane == 0) { y0.y = 0.f; y1.y = 0.f; }   // Re(): self-conjugate bins 0 and N/2
+          }
+          if constexpr (n1 == 15 || n1 == 16) {           // Hermitian part of the pair (N/2-1, N/2+1); the pseudo-bin is 0 on this path
+            if ((n1 == 15 && lane == 31) || (n1 == 16 && lane == 1)) { y0.x *= 0.5f; y0.y *= 0.5f; y1.x *= 0.5f; y1.y *= 0.5f; }
+          }
+          // G = Yh_t + i Yh_{t+1} (j <= N/2), conj(Yh_t) + i conj(Yh_{t+1}) (mirror); parts swapped: IFFT(G) = swap(FFT(swap(G)))
+          const float2 g = mir ? make_float2(y0.x + y1.y, y1.x - y0.y) : make_float2(y0.x - y1.y, y0.y + y1.x);
+          v[brev5(n1)] = make_float2(g.y, g.x);
+        });
+        __syncwarp();
+        if (lane == 0) {   // the spectrum buffer goes back to microphone warp 0
+          sh.nonfinite[ky][0] = 0; sh.nonfinite[ky][1] = 0;
+          __threadfence_block();
+          mbar_arrive(&sh.y_free[ky]);
+        }
       }
+      // ------------------------------------------------------------------ the transform (one code copy for both roles)
       ss_fft1024_fwd(v, tile, sh.tw, lane, [&]() {
         // the exchange tile is free until the next pair: its hops start to arrive now, behind the second FFT pass,
         // the gate and the staging of this pair
@@ -336,9 +410,35 @@ __global__ void __launch_bounds__(kSsThreads, 1) sel_stream_kernel(const __grid_
           issue(t + 2);
         }
       });
+      if (is_inv) {
+        // ---------------------------------------------------------------- synthesis window, overlap-add (util.h:244-253,301-302)
+        float* o0 = p.out + (size_t)s * p.out_stream_stride + (size_t)t * H;
+        const float bad0 = z0 ? __int_as_float(0x7fc00000) : 0.f;
+        const float bad1 = z1 ? __int_as_float(0x7fc00000) : 0.f;
+        static_for<0, 16>([&](auto m2c) {
+          constexpr int m2 = decltype(m2c)::value;
+          const float w0 = win1024<m2>(s_w, c_w);
+          const float w1 = win1024<m2 + 16>(s_w, c_w);
+          const float y0a = v[m2].y * w0 + bad0, y0b = v[m2 + 16].y * w1 + bad0;   // frame t: first / second half
+          const float y1a = v[m2].x * w0 + bad1, y1b = v[m2 + 16].x * w1 + bad1;   // frame t+1
+          o0[32 * m2 + lane] = sh.tail[32 * m2 + lane] + y0a;
+          if (two) o0[H + 32 * m2 + lane] = y0b + y1a;
+          sh.tail[32 * m2 + lane] = two ? y1b : y0b;
+        });
+        continue;
+      }
+      // ================================================================== microphone warps only from here
+      int sx = sig0 + 2 * ip;
+      sx %= Dt;                                     // ring slot of frame t
+      const int sx1 = (sx + 1 == Dt) ? 0 : sx + 1;  // ring slot of frame t+1 (it still holds frame t-P)
       // v[k2] = Z[32*k2 + lane], Z = FFT(0.5*w*(x_t + i x_{t+1})).  X_t[l] = Z[l] + conj(Z[N-l]), X_{t+1}[l] = -i (Z[l] - conj(Z[N-l]));
       // Z[N-l] sits in lane (32 - lane) % 32, register 31 - k2 (lane 0: its own register (32 - k2) % 32).
-      if (m == 0 && ip >= kSsKY) ss_wait(&sh.y_free[ky], (uint32_t)((ip / kSsKY) - 1) & 1u);
+      if (m == 0) {
+        if (ip >= kSsKY) ss_wait(&sh.y_free[ky], (uint32_t)((ip / kSsKY) - 1) & 1u);
+        // a non-finite input sample of microphone 0 makes every default output of the frame non-finite (SURVEY B-10)
+        if (!isfinite(e0)) sh.nonfinite[ky][0] = 1;
+        if (two && !isfinite(e1)) sh.nonfinite[ky][1] = 1;
+      }
       float2 x1[kSsBlocks];
       {
         const int src_lane = (32 - lane) & 31;
@@ -353,16 +453,13 @@ __global__ void __launch_bounds__(kSsThreads, 1) sel_stream_kernel(const __grid_
           const float2 x0 = make_float2(a.x + b.x, a.y - b.y);
           const float2 xb = make_float2(a.y + b.y, b.x - a.x);
           x1[k2] = xb;
-          sh.mags[0][m][l] = sqrt_approx(fmaf(x0.x, x0.x, x0.y * x0.y));
-          sh.mags[1][m][l] = sqrt_approx(fmaf(xb.x, xb.x, xb.y * xb.y));
+          sh.mags[m][0][l] = sqrt_approx(fmaf(x0.x, x0.x, x0.y * x0.y));
+          sh.mags[m][1][l] = sqrt_approx(fmaf(xb.x, xb.x, xb.y * xb.y));
           tmem_st2(tm + (uint32_t)((k2 * kSsSlots + sx) * 2), x0.x, x0.y);   // history append of frame t (mvdr.cpp:99-101)
-          if (m == 0) {   // default outputs: 0.01 X_0 inside the band (mvdr.cpp:96), mvdr's bin 0 passes through (mvdr.cpp:76), else 0
-            const bool inb = sh.inband[l] != 0 && !(ALGO == ALGO_MVDR && l == 0);
-            const float g = inb ? 0.01f : ((ALGO == ALGO_MVDR && l == 0) ? 1.0f : 0.0f);
+          if (m == 0) {   // default outputs (overwritten by the solvers where a bin is selected)
+            const float g = sh.ygain[l];
             sh.y[ky][0][l] = make_float2(g * x0.x, g * x0.y);
             sh.y[ky][1][l] = make_float2(g * xb.x, g * xb.y);
-            if (g != 0.f && !(isfinite(x0.x) && isfinite(x0.y))) sh.nonfinite[ky][0] = 1;
-            if (g != 0.f && two && !(isfinite(xb.x) && isfinite(xb.y))) sh.nonfinite[ky][1] = 1;
           }
         });
       }
@@ -373,13 +470,14 @@ __global__ void __launch_bounds__(kSsThreads, 1) sel_stream_kernel(const __grid_
         float es0 = 0.f, es1 = 0.f;
         for (int ch = 0; ch < M; ch++) { es0 += sh.sqrtE[0][ch]; es1 += sh.sqrtE[1][ch]; }
         const float g0 = 2.0e-5f * es0 + 1.0e-6f * p.thr_mag, g1 = 2.0e-5f * es1 + 1.0e-6f * p.thr_mag;
+#pragma unroll 1
         for (int k2 = m; k2 < kSsBlocks; k2 += kSsMicWarps) {
           const int l = k2 * 32 + lane;
-          const bool inb = sh.inband[l] != 0 && !(ALGO == ALGO_MVDR && l == 0);
+          const bool inb = sh.inband[l] != 0;
           float st0 = 0.f, st1 = 0.f;
 #pragma unroll
           for (int ch = 0; ch < 8; ch++)
-            if (ch < M) { st0 += sh.mags[0][ch][l]; st1 += sh.mags[1][ch][l]; }
+            if (ch < M) { st0 += sh.mags[ch][0][l]; st1 += sh.mags[ch][1][l]; }
           bool f0 = false, f1 = false, r0 = false, r1 = false;
           if (inb) {
             if (fabsf(st0 - p.thr_mag) <= g0) r0 = true;
@@ -389,25 +487,25 @@ __global__ void __launch_bounds__(kSsThreads, 1) sel_stream_kernel(const __grid_
               else if (st1 > p.thr_mag) f1 = true;
             }
           }
-          unsigned rm = __ballot_sync(0xffffffffu, r0);
-          while (rm) {
-            const int b = __ffs(rm) - 1;
-            rm &= rm - 1;
-            const bool sel = ss_gate_fp64(p, s, t, k2 * 32 + b, 0, lane);
-            if (lane == b) f0 = sel;
-          }
-          rm = __ballot_sync(0xffffffffu, r1);
-          while (rm) {
-            const int b = __ffs(rm) - 1;
-            rm &= rm - 1;
-            const bool sel = ss_gate_fp64(p, s, t, k2 * 32 + b, 1, lane);
-            if (lane == b) f1 = sel;
+          unsigned rm = __ballot_sync(0xffffffffu, r0) | (__ballot_sync(0xffffffffu, r1) << 0) * 0u;
+          rm = __ballot_sync(0xffffffffu, r0);
+          unsigned rm1 = __ballot_sync(0xffffffffu, r1);
+#pragma unroll 1
+          while (rm | rm1) {   // rare: exact double DFT of that bin for every microphone, warp-cooperative
+            const int f = rm ? 0 : 1;
+            unsigned& mk = rm ? rm : rm1;
+            const int b = __ffs(mk) - 1;
+            mk &= mk - 1;
+            const bool sel = ss_gate_fp64(p, s, t, k2 * 32 + b, f, lane);
+            if (lane == b) { if (f) f1 = sel; else f0 = sel; }
           }
           const unsigned m0 = __ballot_sync(0xffffffffu, f0), m1 = __ballot_sync(0xffffffffu, f1);
           if (lane == 0) { sh.masks[0][k2] = m0; sh.masks[1][k2] = m1; }
         }
       }
-      named_bar_sync(2, kSsMicWarps * 32);   // selection masks complete
+      named_bar_sync(2, kSsMicWarps * 32);   // selection masks complete; nobody reads the magnitudes any more
+#pragma unroll
+      for (int k2 = 0; k2 < kSsBlocks; k2++) xpark[k2 * 32 + lane] = x1[k2];
       if (p.capture) {   // diagnostics: one byte per FFT bin and frame, bit 0 = selected
         for (int k2 = m; k2 <= 16; k2 += kSsMicWarps) {
           const int l = k2 * 32 + lane;
@@ -434,27 +532,13 @@ __global__ void __launch_bounds__(kSsThreads, 1) sel_stream_kernel(const __grid_
       const int n_items = __shfl_sync(0xffffffffu, pre, kSsBlocks - 1);
       const int base_excl = pre - cnt;
       const int nbat = (n_items + kSsItems - 1) / kSsItems;
-      if (m == 0 && lane == 0) {
-        sh.nbatches[ky] = nbat;
-        mbar_arrive(&sh.y_done[ky]);   // defaults written, batch count known: the inverse warp may start to wait for the solvers
-      }
+      // defaults written, batch count known: this arrival stands for every batch the pair does NOT have (the solvers arrive once per batch)
+      if (m == 0 && lane == 0) mbar_arrive_cnt(&sh.y_done[ky], (uint32_t)(kSsYDoneCount - nbat));
       int cur_q = -1;
-      auto publish = [&](int q) {
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&sh.full[(seq0 + q) % kSsSolvers]);
-      };
-      auto open = [&](int q) {
-        const int n = seq0 + q, b = n % kSsSolvers, round = n / kSsSolvers;
-        if (round >= 1) ss_wait(&sh.empty[b], (uint32_t)(round - 1) & 1u);
-        if (m == 0 && lane == 0) {
-          SsBatch& bt = sh.batch[b];
-          bt.n_items = min(kSsItems, n_items - q * kSsItems);
-          bt.ybuf = ky; bt.t = t; bt.two = two ? 1 : 0;
-        }
-      };
-      static_for<0, kSsBlocks>([&](auto k2c) {
-        constexpr int k2 = decltype(k2c)::value;
+#pragma unroll 1
+      for (int k2 = 0; k2 < kSsBlocks; k2++) {
         const unsigned em = __shfl_sync(0xffffffffu, emask, k2);
+        const float2 xn = xpark[k2 * 32 + lane];
         if (em) {   // warp-uniform
           const int bbase = __shfl_sync(0xffffffffu, base_excl, k2);
           uint32_t r[24];
@@ -464,18 +548,25 @@ __global__ void __launch_bounds__(kSsThreads, 1) sel_stream_kernel(const __grid_
           const bool mine = ((em >> lane) & 1u) != 0;
           const int idx = bbase + __popc(em & ((1u << lane) - 1u));
           const int q_lo = bbase / kSsItems, q_hi = (bbase + __popc(em) - 1) / kSsItems;
+#pragma unroll 1
           for (int q = q_lo; q <= q_hi; q++) {
+            const int n = seq0 + q, bslot = n % kSsSolvers;
+            SsBatch& bt = sh.batch[bslot];
             if (q > cur_q) {
-              if (cur_q >= 0) publish(cur_q);
-              open(q);
+              if (cur_q >= 0) ss_publish((seq0 + cur_q) % kSsSolvers);   // the previous batch is complete for this warp
+              const int round = n / kSsSolvers;
+              if (round >= 1) ss_wait(&sh.empty[bslot], (uint32_t)(round - 1) & 1u);
+              if (m == 0 && lane == 0) {
+                bt.n_items = min(kSsItems, n_items - q * kSsItems);
+                bt.ybuf = ky; bt.t = t; bt.two = two ? 1 : 0;
+              }
               cur_q = q;
             }
             if (mine && idx / kSsItems == q) {
-              SsBatch& bt = sh.batch[(seq0 + q) % kSsSolvers];
               float2* dst = &bt.item[idx % kSsItems][m];
 #pragma unroll
               for (int e = 0; e < kSsSlots; e++) dst[e * 8] = make_float2(__uint_as_float(r[2 * e]), __uint_as_float(r[2 * e + 1]));
-              dst[kSsSlots * 8] = x1[k2];
+              dst[kSsSlots * 8] = xn;
               if (m == 0) {
                 bt.bin[idx % kSsItems] = (unsigned short)(k2 * 32 + lane);
                 bt.flags[idx % kSsItems] = (unsigned char)(((sh.masks[0][k2] >> lane) & 1u) | (((sh.masks[1][k2] >> lane) & 1u) << 1));
@@ -483,17 +574,22 @@ __global__ void __launch_bounds__(kSsThreads, 1) sel_stream_kernel(const __grid_
             }
           }
         }
-        if (two) tmem_st2(tm + (uint32_t)((k2 * kSsSlots + sx1) * 2), x1[k2].x, x1[k2].y);   // history append of frame t+1
-      });
-      if (cur_q >= 0) publish(cur_q);
+        if (two) tmem_st2(tm + (uint32_t)((k2 * kSsSlots + sx1) * 2), xn.x, xn.y);   // history append of frame t+1
+      }
+      if (cur_q >= 0) ss_publish((seq0 + cur_q) % kSsSolvers);
       seq0 += nbat;
       tmem_wait_st();
     }
-    if (m == 0 && lane == 0) {
-      __threadfence_block();
-      *reinterpret_cast<volatile int*>(&sh.total_batches) = seq0;   // the solvers leave once their next batch number reaches this
+    if (is_mic) {
+      // end of the stream: one more arrival per slot releases its solver, which leaves when its next batch number reaches the total
+      if (m == 0 && lane == 0) *reinterpret_cast<volatile int*>(&sh.total_batches) = seq0;
+      for (int w = 0; w < kSsSolvers; w++) {
+        const int rounds = seq0 > w ? (seq0 - w + kSsSolvers - 1) / kSsSolvers : 0;   // batches that went through slot w
+        if (rounds >= 1) ss_wait(&sh.empty[w], (uint32_t)(rounds - 1) & 1u);
+        ss_publish(w);
+      }
     }
-    // ---- state for the next call: the last min(nh, P) frames go back to the global ring ----
+    // ---- state for the next call: the last min(nh, P) frames go back to the global ring; the overlap-add tail ----
     if (have) {
       const int nsave = min(nh, p.P);
       const int a0 = (sig0 + nh - 1) % Dt;           // ring slot (tensor memory) of the launch's last frame
@@ -513,24 +609,21 @@ __global__ void __launch_bounds__(kSsThreads, 1) sel_stream_kernel(const __grid_
           int g = g0 - age;
           if (g < 0) g += D;
           if (e < Dt && age < nsave && ss >= 0)
-            const_cast<float2*>(hist_s)[(size_t)g * slot_stride + ss] = make_float2(__uint_as_float(r[2 * e]), __uint_as_float(r[2 * e + 1]));
+            hist_s[(size_t)g * slot_stride + ss] = make_float2(__uint_as_float(r[2 * e]), __uint_as_float(r[2 * e + 1]));
         }
       }
     }
-  } else if (warp < kSsMicWarps + kSsSolvers) {
+    if (is_inv)
+      for (int i = lane; i < H; i += 32) p.tail[(size_t)s * H + i] = sh.tail[i];
+  } else {
     // ================================================================== solver warps
     const int w = warp - kSsMicWarps;
+#pragma unroll 1
     for (int round = 0;; round++) {
       const int n = w + round * kSsSolvers;
-      bool fin = false;
-      unsigned spins = 0;
-      long long t0 = 0;
-      while (!mbar_try_wait(&sh.full[w], (uint32_t)round & 1u)) {
-        const int tot = *reinterpret_cast<volatile int*>(&sh.total_batches);
-        if (tot >= 0 && n >= tot) { fin = true; break; }
-        ss_watchdog(spins, t0);
-      }
-      if (fin) break;
+      named_bar_sync(kSsBarBase + w, kSsBarThreads);   // blocked in hardware until the eight microphone warps have filled slot w
+      const int tot = *reinterpret_cast<volatile int*>(&sh.total_batches);
+      if (tot >= 0 && n >= tot) break;
       const SsBatch& bt = sh.batch[w];
       const int ky = bt.ybuf;
       ss_solve_batch<ALGO>(p, sh, bt, lane);
@@ -538,84 +631,9 @@ __global__ void __launch_bounds__(kSsThreads, 1) sel_stream_kernel(const __grid_
       if (lane == 0) {
         __threadfence_block();
         mbar_arrive(&sh.empty[w]);
-        atomicAdd(&sh.done_cnt[ky], 1);
+        mbar_arrive(&sh.y_done[ky]);
       }
     }
-  } else {
-    // ================================================================== inverse warp: Hermitian assembly, inverse FFT, overlap-add
-    double sd, cd;
-    sincospi((double)lane / 1024.0, &sd, &cd);
-    const float s_o = (float)(sd * p.out_scale), c_o = (float)(cd * p.out_scale);   // synthesis window * out_amp / N
-    float tl[16];
-#pragma unroll
-    for (int m2 = 0; m2 < 16; m2++) tl[m2] = p.tail[(size_t)s * H + 32 * m2 + lane];
-    for (int ip = 0; ip < npairs; ip++) {
-      const int t = p.hop_begin + 2 * ip;
-      const bool two = t + 1 < p.hop_end;
-      const int ky = ip % kSsKY;
-      ss_wait(&sh.y_done[ky], (uint32_t)(ip / kSsKY) & 1u);
-      if (lane == 0) {
-        const int nb = sh.nbatches[ky];
-        unsigned spins = 0;
-        long long t0 = 0;
-        while (*reinterpret_cast<volatile int*>(&sh.done_cnt[ky]) < nb) {
-          __nanosleep(40);
-          ss_watchdog(spins, t0);
-        }
-        __threadfence_block();
-      }
-      __syncwarp();
-      // one inf/NaN bin makes the reference's whole inverse frame NaN; the two frames of a pair share one complex transform
-      // here, so a poisoned frame is left out of G and re-poisoned at the output without touching its partner
-      const bool z0 = *reinterpret_cast<volatile int*>(&sh.nonfinite[ky][0]) != 0;
-      const bool z1 = *reinterpret_cast<volatile int*>(&sh.nonfinite[ky][1]) != 0;
-      if (z0 || z1 || !two) {   // rare: drop the frame from the shared transform (every in-band bin is rewritten for the next pair anyway)
-        for (int l = lane; l < kL1K; l += 32) {
-          if (z0) sh.y[ky][0][l] = make_float2(0.f, 0.f);
-          if (z1 || !two) sh.y[ky][1][l] = make_float2(0.f, 0.f);
-        }
-        __syncwarp();
-      }
-      float2 v[32];
-      static_for<0, 32>([&](auto n1c) {
-        constexpr int n1 = decltype(n1c)::value;
-        const int j = n1 * 32 + lane;
-        const bool mir = (n1 > 16) || (n1 == 16 && lane != 0);   // bins above N/2: conjugate of bin N - j
-        const int l = mir ? 1024 - j : j;
-        float2 y0 = sh.y[ky][0][l], y1 = sh.y[ky][1][l];
-        if constexpr (n1 == 0 || n1 == 16) {
-          if (lane == 0) { y0.y = 0.f; y1.y = 0.f; }   // Re(): self-conjugate bins 0 and N/2
-        }
-        if constexpr (n1 == 15 || n1 == 16) {           // Hermitian part of the pair (N/2-1, N/2+1); the pseudo-bin is 0 on this path
-          if ((n1 == 15 && lane == 31) || (n1 == 16 && lane == 1)) { y0.x *= 0.5f; y0.y *= 0.5f; y1.x *= 0.5f; y1.y *= 0.5f; }
-        }
-        // G = Yh_t + i Yh_{t+1} (j <= N/2), conj(Yh_t) + i conj(Yh_{t+1}) (mirror); parts swapped: IFFT(G) = swap(FFT(swap(G)))
-        const float2 g = mir ? make_float2(y0.x + y1.y, y1.x - y0.y) : make_float2(y0.x - y1.y, y0.y + y1.x);
-        v[brev5(n1)] = make_float2(g.y, g.x);
-      });
-      __syncwarp();
-      if (lane == 0) {   // the spectrum buffer goes back to microphone warp 0
-        sh.nonfinite[ky][0] = 0; sh.nonfinite[ky][1] = 0; sh.done_cnt[ky] = 0;
-        __threadfence_block();
-        mbar_arrive(&sh.y_free[ky]);
-      }
-      ss_fft1024_fwd(v, sh.itile, sh.tw, lane, []() {});
-      float* o0 = p.out + (size_t)s * p.out_stream_stride + (size_t)t * H;
-      const float bad0 = z0 ? __int_as_float(0x7fc00000) : 0.f;
-      const float bad1 = z1 ? __int_as_float(0x7fc00000) : 0.f;
-      static_for<0, 16>([&](auto m2c) {
-        constexpr int m2 = decltype(m2c)::value;
-        const float w0 = win1024<m2>(s_o, c_o);
-        const float w1 = win1024<m2 + 16>(s_o, c_o);
-        const float y0a = v[m2].y * w0 + bad0, y0b = v[m2 + 16].y * w1 + bad0;   // frame t: first / second half
-        const float y1a = v[m2].x * w0 + bad1, y1b = v[m2 + 16].x * w1 + bad1;   // frame t+1
-        o0[32 * m2 + lane] = tl[m2] + y0a;                                       // util.h:301-302
-        if (two) o0[H + 32 * m2 + lane] = y0b + y1a;
-        tl[m2] = two ? y1b : y0b;
-      });
-    }
-#pragma unroll
-    for (int m2 = 0; m2 < 16; m2++) p.tail[(size_t)s * H + 32 * m2 + lane] = tl[m2];
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -629,7 +647,7 @@ size_t sel_stream_smem() { return sizeof(SsShared) + 128; }
 // 100-16 000 Hz -> bins 3..341) and the pseudo-bin must be outside it.
 bool sel_stream_supported(const KernelParams& p, int algo, const uint8_t* inband_host) {
   if (getenv("BF_SEL_OLD")) return false;
-  if (!(p.H == 512 && p.M <= 8 && p.P >= 1 && p.P + 1 <= kSsSlots && (algo == ALGO_MVDR || algo == ALGO_LCMV) && p.C <= kMaxC)) return false;
+  if (!(p.H == 512 && p.M <= 8 && p.P >= 1 && p.P + 1 <= kSsSlots && algo == ALGO_MVDR)) return false;
   for (int l = kSsBins; l < kL1K; l++)
     if (inband_host[l]) return false;
   return true;
@@ -641,12 +659,11 @@ cudaError_t launch_sel_stream(int algo, const KernelParams& p, cudaStream_t st) 
   void (*k)(KernelParams, int) = nullptr;
   switch (algo) {
     case ALGO_MVDR: k = sel_stream_kernel<ALGO_MVDR>; break;
-    case ALGO_LCMV: k = sel_stream_kernel<ALGO_LCMV>; break;
     default: return cudaErrorNotSupported;
   }
   cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  k<<<p.n_streams, kSsThreads, smem, st>>>(p, use_tma);
+  k<<<p.n_streams, SsCfg<ALGO_MVDR>::kThreads, smem, st>>>(p, use_tma);
   return cudaGetLastError();
 }
 

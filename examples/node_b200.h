@@ -119,8 +119,8 @@ int main(int argc, char *argv[]) {
   cfg.sample_rate = rosjack_sample_rate;                         // rosjack.cpp:134
   cfg.hop = rosjack_window_size;                                 // JACK period; fft_win = 2 * hop (util.h:261)
   cfg.initial_angle = angle;
-  cfg.n_mics = number_of_microphones;
-  for (int i = 0; i < number_of_microphones; i++) {
+  cfg.n_mics = n_inputs;                                         // the library reads every port the node opened
+  for (int i = 0; i < n_inputs; i++) {
     // util.h:116-119 re-referenced x,y to microphone 0 after computing dist/angle from the raw values (SURVEY B-6):
     // the library wants the RAW yaml coordinates
     cfg.mic_x[i] = array_geometry[i]["x"] + (i ? array_geometry[0]["x"] : 0.0);
