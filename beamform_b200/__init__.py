@@ -62,6 +62,7 @@ def lib():
     L.bf_config_init.argtypes = [P(BfConfig), C.c_int]
     L.bf_config_load_yaml.argtypes = [P(BfConfig), C.c_char_p]
     L.bf_config_set.argtypes = [P(BfConfig), C.c_char_p, C.c_char_p]
+    L.bf_config_load_launch.argtypes = [P(BfConfig), C.c_char_p]
     L.bf_create.argtypes = [P(C.c_void_p), P(BfConfig), C.c_uint32]
     L.bf_destroy.argtypes = [C.c_void_p]
     L.bf_destroy.restype = None

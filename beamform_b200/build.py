@@ -56,6 +56,22 @@ def build(force=False, verbose=False):
     return out
 
 
+def build_tools():
+    """tools/bf_offline: the C++ offline file driver (WAV / yaml / launch file in, WAV out) on top of the C ABI."""
+    root = os.path.join(HERE, "..")
+    out = os.path.join(root, "tools", "bf_offline")
+    src = os.path.join(root, "tools", "bf_offline.cpp")
+    if os.path.exists(out) and os.path.getmtime(out) >= max(os.path.getmtime(src), os.path.getmtime(LIB)):
+        return out
+    r = subprocess.run([os.environ.get("CXX", "g++"), "-O2", "-std=c++17", "-o", out, src, "-L" + HERE, "-lbeamform_b200",
+                        "-Wl,-rpath,$ORIGIN/../beamform_b200"], capture_output=True, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout + r.stderr)
+        raise RuntimeError("g++ failed building tools/bf_offline")
+    return out
+
+
 if __name__ == "__main__":
     build(force=True, verbose="-v" in sys.argv)
+    build_tools()
     print(LIB)

@@ -4,6 +4,7 @@
 #include <stdint.h>
 
 #define BF_MAX_MICS_DEV 64
+#define BF_GSS_ROWS 16   /* rows of the gss separation-matrix state: look direction + up to 15 interferers (beamform_config.yaml:43-57) */
 
 namespace bf {
 
@@ -35,6 +36,9 @@ struct KernelParams {
   const float2* das_ceff;   // [M][N]     DAS only: Hermitian-ised effective weights (see capi.cu: build_das_ceff)
   const uint8_t* inband;    // [L]        freq_min <= |freqs[j]| <= freq_max (mvdr.cpp:84)
   int C;                    // K+1 columns of the steering matrix
+  int sel_chunk;            // general gated kernel: microphones transformed per pass (< M: spectra spill to sel_ws)
+  float2* sel_ws;           // [B][M][N] spectra workspace of the general gated kernel when they do not fit shared memory, else null
+  int das_chunk;            // das, frame-size-generic kernel: microphones transformed per pass through shared memory (<= M)
   float out_scale;          // out_amp / N
   // ---- diagnostics ----
   uint8_t* capture;         // [B][n_hops_call][N] or null
@@ -50,7 +54,7 @@ struct KernelParams {
   const int* sel_list;      // [Lsel] -> logical bin
   int Lsel;
   float mu, lambda_mu;      // gss: mu, (1 - lambda*mu)
-  float2* gss_w;            // [B][8][M][Lsel] (bin fastest)
+  float2* gss_w;            // [B][BF_GSS_ROWS][M][Lsel] (bin fastest)
   float gss_dj2_scale;      // 2 * (1/(K+1)) in integer arithmetic (gss.cpp:133) -> 2 for K=0 else 0
   float min_phase_rad, mag_mult, thr_phase_mag;   // phase
   float min_mag;            // phasempf

@@ -34,6 +34,8 @@ bool sel_stream_supported(const KernelParams& p, int algo, const uint8_t* inband
 cudaError_t launch_sel_stream(int algo, const KernelParams& p, cudaStream_t st);
 cudaError_t launch_frames_kernel_n(int algo, const KernelParams& p, cudaStream_t st);
 size_t frames_kernel_n_smem(int N, int M, int algo);
+int frames_kernel_n_das_chunk(int N, int M);
+int frames_kernel_sel_chunk(int N, int M);
 cudaError_t launch_frames_kernel_sel(int algo, const KernelParams& p, cudaStream_t st);
 size_t frames_kernel_sel_smem(int N, int M);
 cudaError_t launch_frames_kernel_mcra(const KernelParams& p, cudaStream_t st);
@@ -62,6 +64,8 @@ static const double kPi = 3.141592653589793238462643383279502884;
 static const double kVSound = 343;
 static const double kRad2Deg = 180.0 / kPi;
 static const double kDeg2Rad = kPi / 180.0;
+
+static const size_t kMaxInterferers = 15;   // beamform_config.yaml:43-57 ships 15 slots; the kernels carry look direction + 15 columns
 
 struct PendingEvent {
   int kind;
@@ -101,6 +105,7 @@ struct bf_handle {
   int Lsel = 0;
   float2* d_hist = nullptr;     // mvdr/lcmv: [B][Lsel][P+2][M]
   float2* d_gss_w = nullptr;    // gss: [B][Lsel][C][M]
+  float2* d_sel_ws = nullptr;   // general gated kernel: [B][M][N] spectra workspace when they do not fit shared memory
   // steered-response sweep workspace
   float2* d_srp_xs = nullptr;
   size_t srp_xs_cap = 0;
@@ -275,6 +280,59 @@ extern "C" int bf_config_load_yaml(bf_config* c, const char* path) {
   return BF_OK;
 }
 
+// A reference launch file (launch/<node>.launch): the node's operating values live in the inline <rosparam> block
+// ("key: value" lines, launch/mvdr.launch:5-11) or in <param name=".." value=".."/> tags; <rosparam command="load" .../>
+// lines point at the yaml files, which bf_config_load_yaml reads.
+extern "C" int bf_config_load_launch(bf_config* c, const char* path) {
+  if (!c || !path) return fail(BF_ERR_INVALID, "bf_config_load_launch: null argument");
+  std::ifstream f(path);
+  if (!f) return fail(BF_ERR_IO, std::string("cannot open ") + path);
+  std::stringstream buf;
+  buf << f.rdbuf();
+  const std::string txt = buf.str();
+  size_t pos = 0;
+  int found = 0;
+  while ((pos = txt.find("<rosparam", pos)) != std::string::npos) {
+    const size_t gt = txt.find('>', pos);
+    if (gt == std::string::npos) break;
+    const bool self_closing = gt > 0 && txt[gt - 1] == '/';
+    pos = gt + 1;
+    if (self_closing) continue;   // command="load" file=...
+    const size_t end = txt.find("</rosparam>", pos);
+    if (end == std::string::npos) return fail(BF_ERR_INVALID, std::string(path) + ": unterminated <rosparam> block");
+    std::stringstream block(txt.substr(pos, end - pos));
+    std::string line;
+    while (std::getline(block, line)) {
+      const size_t hash = line.find('#');
+      if (hash != std::string::npos) line = line.substr(0, hash);
+      const size_t colon = line.find(':');
+      if (colon == std::string::npos) continue;
+      const std::string key = trim(line.substr(0, colon)), val = trim(line.substr(colon + 1));
+      if (key.empty() || val.empty()) continue;
+      bf_config_set(c, key.c_str(), val.c_str());
+      found++;
+    }
+    pos = end;
+  }
+  pos = 0;
+  while ((pos = txt.find("<param", pos)) != std::string::npos) {
+    const size_t gt = txt.find('>', pos);
+    if (gt == std::string::npos) break;
+    const std::string tag = txt.substr(pos, gt - pos);
+    auto attr = [&](const char* name) -> std::string {
+      const size_t a = tag.find(std::string(name) + "=\"");
+      if (a == std::string::npos) return std::string();
+      const size_t b = a + strlen(name) + 2, e = tag.find('"', b);
+      return e == std::string::npos ? std::string() : tag.substr(b, e - b);
+    };
+    const std::string key = attr("name"), val = attr("value");
+    if (!key.empty() && !val.empty()) { bf_config_set(c, key.c_str(), val.c_str()); found++; }
+    pos = gt + 1;
+  }
+  (void)found;   // a launch file without inline parameters is legal (launch/das.launch): the getParam fall-backs stay
+  return BF_OK;
+}
+
 // ------------------------------------------------------------------------------------------------
 // geometry, frequency vector, steering (all double, as the reference)
 // ------------------------------------------------------------------------------------------------
@@ -400,10 +458,10 @@ extern "C" int bf_create(bf_handle** out, const bf_config* cfg, uint32_t n_strea
     // spectra of one frame pair in shared memory
     if (sel && (cfg->hop != 512 || cfg->n_mics > 8) && !(cfg->algo == BF_ALGO_GSS && cfg->hop == 512)) {
       if (cfg->n_mics > 16) return fail(BF_ERR_INVALID, "bf_create: mvdr/lcmv (and gss at this frame size) support at most 16 microphones");
-      if (bf::frames_kernel_sel_smem(2 * (int)cfg->hop, cfg->n_mics) > 232448)
-        return fail(BF_ERR_INVALID, "bf_create: too many microphones for this frame size (spectra must fit 227 KB of shared memory)");
+      if (bf::frames_kernel_sel_smem(2 * (int)cfg->hop, 1) > 232448)
+        return fail(BF_ERR_INVALID, "bf_create: frame size too large for the shared memory");
     }
-    if (!sel && cfg->hop != 512 && bf::frames_kernel_n_smem(2 * (int)cfg->hop, cfg->n_mics, cfg->algo) > 232448)
+    if (!sel && cfg->algo != BF_ALGO_DAS && cfg->hop != 512 && bf::frames_kernel_n_smem(2 * (int)cfg->hop, cfg->n_mics, cfg->algo) > 232448)
       return fail(BF_ERR_INVALID, "bf_create: too many microphones for this frame size (spectra must fit 227 KB of shared memory)");
   }
   if (cfg->algo < 0 || cfg->algo > 8) return fail(BF_ERR_INVALID, "bf_create: unknown algo");
@@ -438,8 +496,12 @@ extern "C" int bf_create(bf_handle** out, const bf_config* cfg, uint32_t n_strea
   h->angle = cfg->initial_angle;
   if (cfg->algo == BF_ALGO_LCMV || cfg->algo == BF_ALGO_GSS) {
     for (int k = 0; k < cfg->n_angle_interf && k < BF_MAX_INTERF; k++) {   // util.h:101-112
-      if (std::fabs(cfg->angle_interf[k]) <= 180) h->interference_angles.push_back(cfg->angle_interf[k]);
-      else break;
+      if (std::fabs(cfg->angle_interf[k]) > 180) break;
+      if (h->interference_angles.size() == kMaxInterferers) {
+        delete h;
+        return fail(BF_ERR_INVALID, "bf_create: at most 15 interferers (beamform_config.yaml ships angle_interf1..15)");
+      }
+      h->interference_angles.push_back(cfg->angle_interf[k]);
     }
   }
   calculate_frequency_vector(h);
@@ -505,7 +567,7 @@ extern "C" int bf_create(bf_handle** out, const bf_config* cfg, uint32_t n_strea
         ok2 = cudaMalloc(&h->d_hist, sizeof(float2) * nh) == cudaSuccess;
         if (ok2) cudaMemset(h->d_hist, 0, sizeof(float2) * nh);   // past_ffts.setZero() (mvdr.cpp:229-233)
       }
-      if (ok2 && cfg->algo == BF_ALGO_GSS) ok2 = cudaMalloc(&h->d_gss_w, sizeof(float2) * (size_t)h->B * nl * 8 * h->M) == cudaSuccess;
+      if (ok2 && cfg->algo == BF_ALGO_GSS) ok2 = cudaMalloc(&h->d_gss_w, sizeof(float2) * (size_t)h->B * nl * BF_GSS_ROWS * h->M) == cudaSuccess;
       if (!ok2) { bf_destroy(h); return fail(BF_ERR_ALLOC, "bf_create: device allocation failed (state)"); }
       cudaMemcpy(h->d_sel_slot, slot.data(), sizeof(int) * h->L, cudaMemcpyHostToDevice);
       if (h->Lsel) cudaMemcpy(h->d_sel_list, list.data(), sizeof(int) * h->Lsel, cudaMemcpyHostToDevice);
@@ -558,7 +620,7 @@ extern "C" void bf_destroy(bf_handle* h) {
   if (h->st_d2h) cudaStreamDestroy(h->st_d2h);
   for (int i = 0; i < 8; i++) { if (h->ev_in[i]) cudaEventDestroy(h->ev_in[i]); if (h->ev_k[i]) cudaEventDestroy(h->ev_k[i]); }
   cudaFree(h->d_steer_d); cudaFree(h->d_mpf_state); cudaFree(h->d_smooth_hist);
-  cudaFree(h->d_sel_slot); cudaFree(h->d_sel_list); cudaFree(h->d_hist); cudaFree(h->d_gss_w); cudaFree(h->d_win_d); cudaFree(h->d_twid_d); cudaFree(h->d_win_f); cudaFree(h->d_twid_f);
+  cudaFree(h->d_sel_ws); cudaFree(h->d_sel_slot); cudaFree(h->d_sel_list); cudaFree(h->d_hist); cudaFree(h->d_gss_w); cudaFree(h->d_win_d); cudaFree(h->d_twid_d); cudaFree(h->d_win_f); cudaFree(h->d_twid_f);
   cudaFree(h->d_srp_xs); cudaFree(h->d_srp_tau); cudaFree(h->d_srp_freqs);
   cudaFree(h->d_gsc_aligned); cudaFree(h->d_gsc_tail); cudaFree(h->d_gsc_state); cudaFree(h->d_gsc_head);
   if (h->h_stage_in) cudaFreeHost(h->h_stage_in);
@@ -593,7 +655,7 @@ static int apply_interference(bf_handle* h, uint16_t id, float msg_angle) {
     int i;
     for (i = 0; i < (int)ia.size(); i++)
       if (std::fabs(ia[i] - msg_angle) < h->cfg.interf_angle_threshold) break;
-    if (i == (int)ia.size() && ia.size() < BF_MAX_INTERF) {
+    if (i == (int)ia.size() && ia.size() < kMaxInterferers) {   // the list is full: the message is dropped (the reference would grow without bound)
       ia.push_back(msg_angle);
       allocate_interf_buffers(h);
       restructured = 1;
@@ -676,6 +738,8 @@ static int run_segment(bf_handle* h, const float* in, size_t ss, size_t ms, floa
   p.frame_index0 = (int)(h->frames_done & 0x7fffffff);
   p.prev_hop = h->d_prev_hop; p.tail = h->d_tail; p.tail_out = h->d_tail;
   p.steer = h->d_steer; p.das_ceff = h->d_das_ceff; p.inband = h->d_inband; p.C = h->C;
+  p.das_chunk = bf::frames_kernel_n_das_chunk((int)h->N, (int)h->M);
+  p.sel_chunk = (int)h->M; p.sel_ws = nullptr;
   // (mcra applies out_amp to the magnitudes itself, like phasempf)
   const bool amp = h->cfg.algo == BF_ALGO_MVDR || h->cfg.algo == BF_ALGO_LCMV || h->cfg.algo == BF_ALGO_GSS;
   p.out_scale = (float)((amp ? h->cfg.out_amp : 1.0) / (double)h->N);
@@ -683,8 +747,6 @@ static int run_segment(bf_handle* h, const float* in, size_t ss, size_t ms, floa
     p.capture = h->d_capture + (size_t)h0 * h->N;
     p.capture_stream_stride = (long long)call_hops * h->N;
   }
-  if (h->C > 8 && (h->cfg.algo == BF_ALGO_LCMV || h->cfg.algo == BF_ALGO_GSS))
-    return fail(BF_ERR_INVALID, "more than 7 interferers are not supported by this build");
   p.thr_mag = (float)(h->cfg.freq_mag_threshold * (double)h->M * (double)h->N);
   p.thr_mag_d = h->cfg.freq_mag_threshold;
   p.P = (int)h->cfg.past_windows;
@@ -748,8 +810,15 @@ static int run_segment(bf_handle* h, const float* in, size_t ss, size_t ms, floa
     h->launches++;
   } else if (h->cfg.algo == BF_ALGO_MCRA) CUDA_TRY(bf::launch_frames_kernel_mcra(p, st));
   else if (h->cfg.algo == BF_ALGO_REF) CUDA_TRY(bf::launch_ref_kernel(p, st));
-  else if (sel_algo && (h->N != 1024 || force_sel_generic || (h->M > 8 && h->cfg.algo != BF_ALGO_GSS)))
+  else if (sel_algo && (h->N != 1024 || force_sel_generic || (h->M > 8 && h->cfg.algo != BF_ALGO_GSS) || h->C > 8)) {   // > 7 interferers: general kernel
+    p.sel_chunk = bf::frames_kernel_sel_chunk((int)h->N, (int)h->M);
+    if (p.sel_chunk < (int)h->M) {
+      if (!h->d_sel_ws && cudaMalloc(&h->d_sel_ws, sizeof(float2) * (size_t)h->B * h->M * h->N) != cudaSuccess)
+        return fail(BF_ERR_ALLOC, "spectra workspace of the general gated kernel");
+      p.sel_ws = h->d_sel_ws;
+    }
     CUDA_TRY(bf::launch_frames_kernel_sel(h->cfg.algo, p, st));
+  }
   else if (h->N != 1024 || (force_generic && gen_algo)) CUDA_TRY(bf::launch_frames_kernel_n(h->cfg.algo, p, st));
   else if (h->cfg.algo == BF_ALGO_DAS && bf::das_pairs_supported(p)) {
     // a stream's first and last pair may belong to different warps: the new tails go to the second buffer (no

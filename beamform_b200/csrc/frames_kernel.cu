@@ -217,7 +217,7 @@ __global__ void save_prev_hop_kernel(const KernelParams p, int last_hop) {
 
 // gss.cpp:90-93: every update_weights resets sep_matrix[j] = weights[j]^H (adaptation is discarded)
 __global__ void gss_reset_kernel(const KernelParams p) {
-  // state layout [B][8][M][Lsel] (bin fastest); only the first C rows are live
+  // state layout [B][BF_GSS_ROWS][M][Lsel] (bin fastest); only the first C rows are live
   const size_t per = (size_t)p.C * p.M * p.Lsel;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < (size_t)p.n_streams * per; i += (size_t)gridDim.x * blockDim.x) {
     const size_t sidx = i / per, r = i % per;
@@ -225,7 +225,7 @@ __global__ void gss_reset_kernel(const KernelParams p) {
     const int cm = (int)(r / p.Lsel), c = cm / p.M, m = cm % p.M;
     const int l = p.sel_list[slot];
     const float2 a = p.steer[((size_t)l * p.C + c) * p.M + m];
-    p.gss_w[sidx * 8 * p.M * p.Lsel + (size_t)cm * p.Lsel + slot] = make_float2(a.x, -a.y);
+    p.gss_w[sidx * BF_GSS_ROWS * p.M * p.Lsel + (size_t)cm * p.Lsel + slot] = make_float2(a.x, -a.y);
   }
 }
 cudaError_t launch_gss_reset(const KernelParams& p, cudaStream_t st) {

@@ -629,8 +629,9 @@ __global__ void __launch_bounds__(kGenThreads, 1) frames_kernel_n(const __grid_c
   typedef typename std::conditional<kPha, double2, float2>::type ZV;   // forward spectra: double for the phase masks
   unsigned char* smem_raw = gen_smem_raw;
   ZV* zall = reinterpret_cast<ZV*>(smem_raw);                            // [M][NN]
-  float2* gbuf = reinterpret_cast<float2*>(zall + (size_t)p.M * NN);     // [NN]
-  const unsigned g_off = (unsigned)((size_t)p.M * NN * sizeof(ZV));
+  const int m_tiles = (ALGO == ALGO_DAS) ? p.das_chunk : p.M;             // spectrum tiles resident at once
+  float2* gbuf = reinterpret_cast<float2*>(zall + (size_t)m_tiles * NN);   // [NN]
+  const unsigned g_off = (unsigned)((size_t)m_tiles * NN * sizeof(ZV));
   GenScratch<NN>& sc = *reinterpret_cast<GenScratch<NN>*>(gbuf + NN);
   const int tid = threadIdx.x;
   const int M = p.M;
@@ -712,31 +713,38 @@ __global__ void __launch_bounds__(kGenThreads, 1) frames_kernel_n(const __grid_c
         }
       });
     };
-    for (int ch = 0; ch < M; ch += 2) {   // two microphones' loads in flight per round trip
+    // das is linear in the spectra (das.cpp:60-63), so large arrays go through the shared-memory tile in chunks of Mc
+    // microphones and accumulate into G; every other node needs all M spectra of a bin at once (Mc == M)
+    const int Mc = (ALGO == ALGO_DAS) ? p.das_chunk : M;
+    for (int c0 = 0; c0 < M; c0 += Mc) {
+    const int Mn = min(Mc, M - c0);
+    if (c0 > 0) __syncthreads();   // the previous chunk's accumulation has read its spectra
+    for (int cc = 0; cc < Mn; cc += 2) {   // two microphones' loads in flight per round trip
       float fa0[kIter], fb0[kIter], fc0[kIter], fa1[kIter], fb1[kIter], fc1[kIter];
-      pack_load(ch, fa0, fb0, fc0);
-      if (BF_GEN_PACK_PAIR && ch + 1 < M) pack_load(ch + 1, fa1, fb1, fc1);
-      pack_store(ch, fa0, fb0, fc0);
-      if (!BF_GEN_PACK_PAIR && ch + 1 < M) pack_load(ch + 1, fa1, fb1, fc1);
-      if (ch + 1 < M) pack_store(ch + 1, fa1, fb1, fc1);
+      pack_load(c0 + cc, fa0, fb0, fc0);
+      if (BF_GEN_PACK_PAIR && cc + 1 < Mn) pack_load(c0 + cc + 1, fa1, fb1, fc1);
+      pack_store(cc, fa0, fb0, fc0);
+      if (!BF_GEN_PACK_PAIR && cc + 1 < Mn) pack_load(c0 + cc + 1, fa1, fb1, fc1);
+      if (cc + 1 < Mn) pack_store(cc + 1, fa1, fb1, fc1);
     }
     __syncthreads();
     BF_PHASE(0);
-    if constexpr (kPha) block_fft_fn<NN, -1, double2>(0u, M, p.twid_d, tid);
-    else block_fft_fn<NN, -1, float2>(0u, M, tw, tid);
+    if constexpr (kPha) block_fft_fn<NN, -1, double2>(0u, Mn, p.twid_d, tid);
+    else block_fft_fn<NN, -1, float2>(0u, Mn, tw, tid);
     BF_PHASE(1);
     // ---- per-bin beamformer ----
     if constexpr (ALGO == ALGO_DAS) {
       // das.cpp:60-63 commutes with the frame packing: G[j] = sum_i ceff_i[j] * Z_i[j] over all N bins
       for (int j = tid; j < NN; j += kGenThreads) {
         float2 acc = make_float2(0.f, 0.f);
-        for (int ch = 0; ch < M; ch++) {
+        for (int ch = 0; ch < Mn; ch++) {
           const float2 z = zall[(size_t)ch * NN + swz(j)];
-          const float2 w = __ldg(p.das_ceff + (size_t)ch * NN + j);
+          const float2 w = __ldg(p.das_ceff + (size_t)(c0 + ch) * NN + j);
           acc.x = fmaf(z.x, w.x, acc.x); acc.x = fmaf(-z.y, w.y, acc.x);
           acc.y = fmaf(z.x, w.y, acc.y); acc.y = fmaf(z.y, w.x, acc.y);
         }
-        gbuf[swz(j)] = make_float2(2.0f * acc.x, 2.0f * acc.y);
+        const float2 prev = c0 > 0 ? gbuf[swz(j)] : make_float2(0.f, 0.f);
+        gbuf[swz(j)] = make_float2(prev.x + 2.0f * acc.x, prev.y + 2.0f * acc.y);
       }
     } else {
       if (M >= 2 && M <= 4) {
@@ -772,6 +780,7 @@ __global__ void __launch_bounds__(kGenThreads, 1) frames_kernel_n(const __grid_c
       }
       }
     }
+    }   // microphone chunks
     __syncthreads();
     BF_PHASE(2);
     // the spectra are consumed: their storage is the second buffer of an out-of-place inverse (one barrier per pass)
@@ -947,7 +956,7 @@ __device__ __noinline__ float2 sel_item_d(const KernelParams& p, const float2* r
   double2 u[kSelMaxM];
   for (int i = 0; i < M; i++) u[i] = make_double2((double)x[i].x, (double)x[i].y);
   fwd(u);
-  double2 V[kMaxC][kSelMaxM], G[kMaxC][kMaxC], b[kMaxC];
+  double2 V[kMaxCGen][kSelMaxM], G[kMaxCGen][kMaxCGen], b[kMaxCGen];
   for (int c = 0; c < C; c++) {
     for (int i = 0; i < M; i++) { const float2 a = steer_l[(size_t)c * M + i]; V[c][i] = make_double2((double)a.x, (double)a.y); }
     fwd(V[c]);
@@ -958,7 +967,7 @@ __device__ __noinline__ float2 sel_item_d(const KernelParams& p, const float2* r
     const double den = G[0][0].x;
     return make_float2((float)(b[0].x / den), (float)(b[0].y / den));
   }
-  double gd[kMaxC];
+  double gd[kMaxCGen];
   for (int j = 0; j < C; j++) {   // Cholesky of G
     double d = G[j][j].x;
     for (int k = 0; k < j; k++) d -= G[j][k].x * G[j][k].x + G[j][k].y * G[j][k].y;
@@ -973,7 +982,7 @@ __device__ __noinline__ float2 sel_item_d(const KernelParams& p, const float2* r
       G[i][j] = make_double2(acc.x * gd[j], acc.y * gd[j]);
     }
   }
-  double2 q[kMaxC], g[kMaxC];
+  double2 q[kMaxCGen], g[kMaxCGen];
   for (int i = 0; i < C; i++) {   // q = Lg^{-1} e0
     double2 acc = make_double2(i == 0 ? 1.0 : 0.0, 0.0);
     for (int k = 0; k < i; k++) {
@@ -1004,13 +1013,18 @@ template <int ALGO, int NN>
 __global__ void __launch_bounds__(kGenThreads, 1) frames_kernel_sel(const __grid_constant__ KernelParams p) {
   constexpr int H = NN / 2, L = NN / 2 + 2;
   unsigned char* smem_raw = gen_smem_raw;
-  float2* zall = reinterpret_cast<float2*>(smem_raw);                     // [M][NN] packed spectra
-  float2* gbuf = zall + (size_t)p.M * NN;                                  // [NN]
+  // Spectra of all M microphones stay in shared memory when they fit (Mc == M).  Otherwise (e.g. 8 microphones at 4096
+  // points: 256 KB) the transforms run Mc microphones at a time through the shared-memory tiles and the finished spectra go to
+  // a per-stream workspace in global memory (L2-resident: it is re-read by the per-bin stage right away).
+  const int Mc = p.sel_chunk;
+  float2* ztile = reinterpret_cast<float2*>(smem_raw);                    // [Mc][NN] transform tiles
+  float2* gbuf = ztile + (size_t)Mc * NN;                                  // [NN]
   SelGenScratch<NN>& sc = *reinterpret_cast<SelGenScratch<NN>*>(gbuf + NN);
-  const unsigned g_off = (unsigned)((size_t)p.M * NN * sizeof(float2));
+  const unsigned g_off = (unsigned)((size_t)Mc * NN * sizeof(float2));
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int M = p.M, D = p.ring_depth;
   const int s = blockIdx.x + p.stream_begin;
+  float2* zall = (Mc < M) ? p.sel_ws + (size_t)s * M * NN : ztile;        // [M][NN] packed spectra
   const float2* tw = p.twid_f;
   const float* win = p.win_f;
 
@@ -1026,27 +1040,37 @@ __global__ void __launch_bounds__(kGenThreads, 1) frames_kernel_sel(const __grid
     if (tid == 0) { sc.n_items = 0; sc.n_recheck = 0; sc.nonfinite[0] = 0; sc.nonfinite[1] = 0; }
     __syncthreads();
     // ---- window + pack (util.h:217-242), frame energies ----
-    for (int ch = 0; ch < M; ch++) {
-      const float* base = p.in + (size_t)s * p.in_stream_stride + (size_t)ch * p.in_mic_stride;
-      const float* ha = (t - 1 < 0) ? p.prev_hop + ((size_t)s * M + ch) * H : base + (size_t)(t - 1) * H;
-      const float* hb = base + (size_t)t * H;
-      const float* hc = two ? base + (size_t)(t + 1) * H : hb;
-      float e0 = 0.f, e1 = 0.f;
-      for (int n = tid; n < H; n += kGenThreads) {
-        const float a = __ldg(ha + n), b = __ldg(hb + n), c = two ? __ldg(hc + n) : 0.f;
-        const float w0 = 0.5f * __ldg(win + n), w1 = 0.5f * __ldg(win + n + H);
-        const float2 z0 = make_float2(a * w0, (two ? b : 0.f) * w0), z1 = make_float2(b * w1, c * w1);
-        zall[(size_t)ch * NN + swz(n)] = z0;
-        zall[(size_t)ch * NN + swz(n + H)] = z1;
-        e0 += z0.x * z0.x + z1.x * z1.x;
-        e1 += z0.y * z0.y + z1.y * z1.y;
-      }
+    for (int c0 = 0; c0 < M; c0 += Mc) {
+      const int Mn = min(Mc, M - c0);
+      for (int cc = 0; cc < Mn; cc++) {
+        const int ch = c0 + cc;
+        const float* base = p.in + (size_t)s * p.in_stream_stride + (size_t)ch * p.in_mic_stride;
+        const float* ha = (t - 1 < 0) ? p.prev_hop + ((size_t)s * M + ch) * H : base + (size_t)(t - 1) * H;
+        const float* hb = base + (size_t)t * H;
+        const float* hc = two ? base + (size_t)(t + 1) * H : hb;
+        float e0 = 0.f, e1 = 0.f;
+        for (int n = tid; n < H; n += kGenThreads) {
+          const float a = __ldg(ha + n), b = __ldg(hb + n), c = two ? __ldg(hc + n) : 0.f;
+          const float w0 = 0.5f * __ldg(win + n), w1 = 0.5f * __ldg(win + n + H);
+          const float2 z0 = make_float2(a * w0, (two ? b : 0.f) * w0), z1 = make_float2(b * w1, c * w1);
+          ztile[(size_t)cc * NN + swz(n)] = z0;
+          ztile[(size_t)cc * NN + swz(n + H)] = z1;
+          e0 += z0.x * z0.x + z1.x * z1.x;
+          e1 += z0.y * z0.y + z1.y * z1.y;
+        }
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) { e0 += __shfl_xor_sync(0xffffffffu, e0, o); e1 += __shfl_xor_sync(0xffffffffu, e1, o); }
-      if (lane == 0) { atomicAdd(&sc.esq[0][ch], e0); atomicAdd(&sc.esq[1][ch], e1); }
+        for (int o = 16; o > 0; o >>= 1) { e0 += __shfl_xor_sync(0xffffffffu, e0, o); e1 += __shfl_xor_sync(0xffffffffu, e1, o); }
+        if (lane == 0) { atomicAdd(&sc.esq[0][ch], e0); atomicAdd(&sc.esq[1][ch], e1); }
+      }
+      __syncthreads();
+      block_fft_fn<NN, -1, float2>(0u, Mn, tw, tid);
+      if (Mc < M) {   // spill the chunk's spectra (same swizzled order) to the global workspace
+        __syncthreads();
+        for (int i = tid; i < Mn * NN; i += kGenThreads) zall[(size_t)c0 * NN + i] = ztile[i];
+        __syncthreads();
+      }
     }
-    __syncthreads();
-    block_fft_fn<NN, -1, float2>(0u, M, tw, tid);
+    if (Mc < M) __threadfence_block();
     const int fr0 = (p.ring_slot0 + (t - p.hop_begin)) % D;   // ring slot of frame t
     // ---- B1: gate, history append, defaults ----
     float es0 = 0.f, es1 = 0.f;
@@ -1114,7 +1138,7 @@ __global__ void __launch_bounds__(kGenThreads, 1) frames_kernel_sel(const __grid
       const float2* steer_l = p.steer + (size_t)l * p.C * M;
       float2 x[kSelMaxM];
       if (ALGO == ALGO_GSS) {
-        float2* Wg = p.gss_w + (size_t)s * 8 * M * p.Lsel + p.sel_slot[l];   // [B][8][M][Lsel]
+        float2* Wg = p.gss_w + (size_t)s * BF_GSS_ROWS * M * p.Lsel + p.sel_slot[l];   // [B][BF_GSS_ROWS][M][Lsel]
         for (int ff = 0; ff < nf; ff++) {
           if (!sc.flag[ff][l]) continue;
           for (int ch = 0; ch < M; ch++) {
@@ -1122,7 +1146,7 @@ __global__ void __launch_bounds__(kGenThreads, 1) frames_kernel_sel(const __grid
             unpack2_n<NN>(zall + (size_t)ch * NN, l, a, b);
             x[ch] = ff ? b : a;
           }
-          sc.y[ff][l] = gss_item(p, Wg, (size_t)p.Lsel, x, steer_l);
+          sc.y[ff][l] = gss_item<kMaxCGen>(p, Wg, (size_t)p.Lsel, x, steer_l);
         }
       } else {
         for (int ch = 0; ch < M; ch++) {
@@ -1198,6 +1222,14 @@ __global__ void __launch_bounds__(kGenThreads, 1) frames_kernel_sel(const __grid
 template <int NN>
 static size_t sel_gen_smem(int M) { return sizeof(float2) * ((size_t)M + 1) * NN + sizeof(SelGenScratch<NN>) + 16; }
 
+size_t frames_kernel_sel_smem(int N, int M);
+// microphones transformed per pass: all of them when their spectra fit the shared memory, else as many as fit
+int frames_kernel_sel_chunk(int N, int M) {
+  int mc = M;
+  while (mc > 1 && frames_kernel_sel_smem(N, mc) > 232448) mc--;
+  return mc;
+}
+
 size_t frames_kernel_sel_smem(int N, int M) {
   switch (N) {
     case 512: return sel_gen_smem<512>(M);
@@ -1210,7 +1242,7 @@ size_t frames_kernel_sel_smem(int N, int M) {
 
 template <int ALGO, int NN>
 static cudaError_t launch_sel_n(const KernelParams& p, cudaStream_t st) {
-  const size_t smem = sel_gen_smem<NN>(p.M);
+  const size_t smem = sel_gen_smem<NN>(p.sel_chunk);
   cudaError_t e = cudaFuncSetAttribute(frames_kernel_sel<ALGO, NN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   frames_kernel_sel<ALGO, NN><<<p.n_streams, kGenThreads, smem, st>>>(p);
@@ -1227,7 +1259,7 @@ static cudaError_t launch_sel_algo(const KernelParams& p, cudaStream_t st) {
   return cudaErrorNotSupported;
 }
 cudaError_t launch_frames_kernel_sel(int algo, const KernelParams& p, cudaStream_t st) {
-  if (p.M > kSelMaxM || p.C > kMaxC) return cudaErrorNotSupported;
+  if (p.M > kSelMaxM || p.C > kMaxCGen) return cudaErrorNotSupported;
   switch (algo) {
     case ALGO_MVDR: return launch_sel_algo<ALGO_MVDR>(p, st);
     case ALGO_LCMV: return launch_sel_algo<ALGO_LCMV>(p, st);
@@ -1772,8 +1804,17 @@ cudaError_t launch_gsc(const KernelParams& p, cudaStream_t st) {
   return cudaGetLastError();
 }
 
+size_t frames_kernel_n_smem(int N, int M, int algo);
+size_t frames_kernel_sel_smem(int N, int M);
 template <int NN>
 static size_t gen_smem(int M, bool pha) { return (pha ? sizeof(double2) : sizeof(float2)) * (size_t)M * NN + sizeof(float2) * NN + sizeof(GenScratch<NN>) + 16; }
+
+// das: the largest number of microphones whose spectra fit the shared memory together (the others follow in further chunks)
+int frames_kernel_n_das_chunk(int N, int M) {
+  int mc = M;
+  while (mc > 1 && frames_kernel_n_smem(N, mc, ALGO_DAS) > 232448) mc--;
+  return mc;
+}
 
 size_t frames_kernel_n_smem(int N, int M, int algo) {
   const bool pha = algo == ALGO_PHASE || algo == ALGO_PHASEMPF;
@@ -1788,7 +1829,7 @@ size_t frames_kernel_n_smem(int N, int M, int algo) {
 
 template <int ALGO, int NN>
 static cudaError_t launch_n(const KernelParams& p, cudaStream_t st) {
-  const size_t smem = gen_smem<NN>(p.M, ALGO == ALGO_PHASE || ALGO == ALGO_PHASEMPF);
+  const size_t smem = gen_smem<NN>(ALGO == ALGO_DAS ? p.das_chunk : p.M, ALGO == ALGO_PHASE || ALGO == ALGO_PHASEMPF);
   cudaError_t e = cudaFuncSetAttribute(frames_kernel_n<ALGO, NN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   frames_kernel_n<ALGO, NN><<<p.n_streams, kGenThreads, smem, st>>>(p);

@@ -17,7 +17,8 @@ namespace bf {
 
 constexpr int kL1K = 514;   // logical bins for N = 1024: 0..512 and the pseudo-bin 513
 constexpr int kMaxMSel = 8; // register-resident solves
-constexpr int kMaxC = 8;
+constexpr int kMaxC = 8;     // columns of the constraint matrix on the register-resident kernels (look direction + 7 interferers)
+constexpr int kMaxCGen = 16; // general gated kernel: look direction + the 15 interferer slots beamform_config.yaml ships
 
 struct SelScratch {
   float2 y[2][kL1K];
@@ -258,9 +259,10 @@ __device__ __forceinline__ float2 lcmv_item(const KernelParams& p, const float2*
 // gss.cpp:118-137 for one selected frame of one bin; W (C x M) lives in global memory (L2-resident between
 // frames), element (c, i) at Wg[(c*M + i) * ws]: the bin index is the fastest axis of the state array so that
 // neighbouring threads (= neighbouring bins) touch neighbouring addresses.  Returns y_0.
+template <int MAXC = kMaxC>
 __device__ __forceinline__ float2 gss_item(const KernelParams& p, float2* Wg, size_t ws, const float2* x, const float2* steer_l) {
   const int C = p.C, M = p.M;
-  float2 y[kMaxC];
+  float2 y[MAXC];
   float alpha = 0.f;
   for (int i = 0; i < M; i++) alpha += x[i].x * x[i].x + x[i].y * x[i].y;
   alpha *= alpha;
@@ -273,7 +275,7 @@ __device__ __forceinline__ float2 gss_item(const KernelParams& p, float2* Wg, si
   float tot = 0.f;
   for (int c = 0; c < C; c++) tot += y[c].x * y[c].x + y[c].y * y[c].y;
   const float s1 = (float)(4 * C) / alpha;   // gss.cpp:132
-  float2 wa[kMaxC];
+  float2 wa[MAXC];
   for (int r = 0; r < C; r++) {
     const float e = s1 * (tot - (y[r].x * y[r].x + y[r].y * y[r].y));
     const float2 ey = make_float2(e * y[r].x, e * y[r].y);

@@ -427,7 +427,7 @@ __global__ void __launch_bounds__(kSelThreads, ALGO == ALGO_LCMV ? 1 : 2) sel_pa
         const int l = sc.items[q] >> 1;
         const int slot = p.sel_slot[l];
         const float2* steer_l = p.steer + (size_t)l * p.C * M;
-        float2* Wg = p.gss_w + (size_t)s * 8 * M * p.Lsel + slot;   // [B][8][M][Lsel]
+        float2* Wg = p.gss_w + (size_t)s * BF_GSS_ROWS * M * p.Lsel + slot;   // [B][BF_GSS_ROWS][M][Lsel]
         for (int ff = 0; ff < nf; ff++) {
           if (!sc.flag[ff][l]) continue;
           float2 x[8];

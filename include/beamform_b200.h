@@ -100,6 +100,7 @@ typedef struct bf_handle bf_handle;
 int bf_config_init(bf_config* cfg, int algo);
 int bf_config_load_yaml(bf_config* cfg, const char* path);            /* beamform_config.yaml */
 int bf_config_set(bf_config* cfg, const char* key, const char* value); /* one rosparam key */
+int bf_config_load_launch(bf_config* cfg, const char* path);           /* launch/<node>.launch: the inline <rosparam> block / <param> tags */
 
 /* --- lifecycle: replaces handle_params + <algo>_handle_params + prepare_overlap_and_add +
  *     fftw_plan_dft_1d + update_weights(true) in every node's main() (das.cpp:102-140) -------- */

@@ -105,3 +105,49 @@ def test_plain_config_table_matches_bf_config_init():
                 assert list(a) == list(b), (algo, name)
             else:
                 assert a == b, (algo, name, a, b)
+
+
+def test_launch_file_reader_matches_launch_table(tmp_path):
+    """bf_config_load_launch reads the inline <rosparam> block of a reference launch file (launch/mvdr.launch:5-11) and <param> tags."""
+    from beamform_b200 import tables
+    for algo, kv in tables.LAUNCH_PARAMS.items():
+        body = "".join("      %s: %s\n" % (k, ("true" if v else "false") if isinstance(v, bool) else v) for k, v in kv.items())
+        f = tmp_path / (algo + ".launch")
+        f.write_text('<launch>\n  <node name="beamform" pkg="beamform" type="%s" output="screen">\n'
+                     '    <rosparam command="load" file="$(find beamform)/beamform_config.yaml" />\n    <rosparam>\n%s    </rosparam>\n  </node>\n</launch>\n' % (algo, body))
+        cfg = bf.BfConfig()
+        assert bf.lib().bf_config_init(C.byref(cfg), bf.ALGOS[algo]) == 0
+        assert bf.lib().bf_config_load_launch(C.byref(cfg), str(f).encode()) == 0
+        ref = bf.make_config(algo, mics="aira3")
+        for name in ("past_windows", "freq_mag_threshold", "freq_max", "freq_min", "out_amp", "interf_angle_threshold", "mu", "lambda_", "min_phase",
+                     "min_mag", "smooth_size", "MCRA_alphaS", "MCRA_alphaD2", "MCRA_L", "MPF_alphaS", "MPF_rev_gamma", "noise_floor", "out_only_noise",
+                     "use_vad", "mu0", "mu_max", "filter_size"):
+            assert getattr(cfg, name) == getattr(ref, name), (algo, name)
+    g = tmp_path / "p.launch"
+    g.write_text('<launch><node name="b" pkg="beamform" type="mvdr"><param name="freq_max" value="8000"/><param name="past_windows" value="6" /></node></launch>')
+    cfg = bf.BfConfig()
+    bf.lib().bf_config_init(C.byref(cfg), 1)
+    assert bf.lib().bf_config_load_launch(C.byref(cfg), str(g).encode()) == 0
+    assert (cfg.freq_max, cfg.past_windows) == (8000.0, 6)
+    assert bf.lib().bf_config_load_launch(C.byref(cfg), b"/nonexistent.launch") != 0
+
+
+def test_offline_tool_fails_loudly_without_a_gpu(tmp_path):
+    """tools/bf_offline parses its arguments, the WAV and the parameter files on any machine; with no B200 bf_create reports
+    BF_ERR_NO_DEVICE and the tool exits 1 with the message (no CPU fallback)."""
+    import subprocess
+    import numpy as np
+    from scipy.io import wavfile
+    from beamform_b200 import build
+    exe = build.build_tools()
+    y = tmp_path / "c.yaml"
+    y.write_text("initial_angle: 0\nmic0: {id: 1, x: 0.0, y: 0.0}\nmic1: {id: 2, x: 0.0, y: -0.18}\n")
+    wavfile.write(str(tmp_path / "in.wav"), 48000, np.zeros((2048, 2), dtype=np.int16))
+    r = subprocess.run([exe, "--algo", "das", "--config", str(y), "--in", str(tmp_path / "in.wav"), "--out", str(tmp_path / "o.wav")], capture_output=True, text=True)
+    import torch
+    if torch.cuda.is_available():
+        assert r.returncode == 0
+    else:
+        assert r.returncode == 1 and "no CUDA device" in r.stderr
+    r = subprocess.run([exe, "--algo", "das", "--config", str(y), "--in", str(y), "--out", str(tmp_path / "o.wav")], capture_output=True, text=True)
+    assert r.returncode == 1 and "RIFF" in r.stderr

@@ -463,8 +463,17 @@ def test_c1_sixty_second_stream_matches_oracle():
     assert err <= REL_L2_TOL
 
 
+def _launch_text(algo):
+    """A launch file in the reference's layout (launch/mvdr.launch:1-13) carrying the node's <rosparam> block."""
+    from beamform_b200 import tables
+    body = "".join("      %s: %s\n" % (k, ("true" if v else "false") if isinstance(v, bool) else v) for k, v in tables.LAUNCH_PARAMS[algo].items())
+    return ('<launch>\n  <node name="beamform" pkg="beamform" type="%s" output="screen">\n    <rosparam command="load" file="$(find beamform)/rosjack_config.yaml" />\n'
+            '    <rosparam command="load" file="$(find beamform)/beamform_config.yaml" />\n    <rosparam>\n%s    </rosparam>\n  </node>\n</launch>\n' % (algo, body))
+
+
 def test_offline_file_driver(tmp_path):
-    """tools/beamform_file.py: wav + beamform_config.yaml in, wav out (the stand-in for the JACK/ROS transport)."""
+    """tools/bf_offline (C++): wav + beamform_config.yaml + launch file in, wav out (the stand-in for the JACK/ROS transport);
+    tools/beamform_file.py is its wrapper."""
     import subprocess
     import sys as _sys
     from scipy.io import wavfile
@@ -481,17 +490,55 @@ def test_offline_file_driver(tmp_path):
     ref = Oracle(cfg).process(x[:, :40 * H], events=[(15, "theta", -30.0)])
     assert sr == 48000 and got.shape == ref.shape
     assert finite_rel_l2(got, ref) <= REL_L2_TOL
+    # the C++ tool itself: launch file, event file, 16-bit PCM input, raw float32 output
+    (tmp_path / "lcmv.launch").write_text(_launch_text("lcmv"))
+    (tmp_path / "events.txt").write_text("12 theta 15.0\n20 interf 1 60.0\n")
+    xy8 = bf.GEOMETRIES["circ8"]
+    x8 = synth_stream(xy8, 36 * H, seed=0xF12E)
+    q = np.clip(np.round(x8 * 32768.0), -32768, 32767).astype(np.int16)
+    wavfile.write(str(tmp_path / "in16.wav"), 48000, q.T)
+    yaml8 = tmp_path / "circ8.yaml"
+    yaml8.write_text("initial_angle: 0.0\n" + "".join("mic%d: {id: %d, x: %r, y: %r}\n" % (i, i + 1, px, py) for i, (px, py) in enumerate(xy8)) + "angle_interf1: 80\nangle_interf2: 181\n")
+    subprocess.run([_os.path.join(root, "tools", "bf_offline"), "--algo", "lcmv", "--config", str(yaml8), "--launch", str(tmp_path / "lcmv.launch"), "--in", str(tmp_path / "in16.wav"),
+                    "--out", str(tmp_path / "out.f32"), "--events", str(tmp_path / "events.txt")], check=True)
+    got = np.fromfile(str(tmp_path / "out.f32"), dtype=np.float32)
+    cfg8 = bf.make_config("lcmv", mics="circ8", interferers=(80.0,))
+    ref = Oracle(cfg8).process(q.astype(np.float32) / 32768.0, events=[(12, "theta", 15.0), (20, "interf", 1, 60.0)])
+    assert got.shape == ref.shape and finite_rel_l2(got, ref) <= REL_L2_TOL
 
 
 def test_unsupported_shapes_fail_loudly():
     with pytest.raises(bf.BeamformError):
-        bf.Beamformer(bf.make_config("mvdr", mics="circ8", hop=2048), 1)      # 8 x 4096-point spectra exceed shared memory
-    with pytest.raises(bf.BeamformError):
         bf.Beamformer(bf.make_config("mvdr", mics="grid64"), 1)               # solves are built for <= 16 microphones
     with pytest.raises(bf.BeamformError):
-        bf.Beamformer(bf.make_config("das", mics="circ8", hop=2048), 1)       # 8 x 4096-point spectra exceed shared memory
+        bf.Beamformer(bf.make_config("phasempf", mics="circ16", hop=2048), 1)   # the phase mask needs all 16 x 4096-point FP64 spectra of a bin at once
     with pytest.raises(bf.BeamformError):
-        bf.Beamformer(bf.make_config("das", mics="aira3", hop=300), 1)
+        bf.Beamformer(bf.make_config("das", mics="aira3", hop=300), 1)        # JACK periods are powers of two (256..2048)
+    with pytest.raises(bf.BeamformError):
+        bf.Beamformer(bf.make_config("lcmv", mics="circ8", interferers=tuple(range(-160, 160, 20))), 1)   # 16 interferers: the yaml ships 15 slots
+
+
+@pytest.mark.parametrize("algo,mics,hop,interf,events", [
+    ("das", "circ8", 2048, (), ()), ("das", "circ16", 2048, (), ((9, "theta", 40.0),)), ("das", "circ16", 1024, (), ()),
+    ("mvdr", "circ8", 2048, (), ()), ("lcmv", "circ8", 2048, (80.0, -60.0, 150.0), ((11, "interf", 2, -55.0),)),
+    ("lcmv", "circ16", 512, tuple(-170.0 + 34.0 * k for k in range(10)), ((15, "interf", 11, 5.0), (25, "interf", 3, -100.5))),
+    ("gss", "circ12", 512, tuple(-150.0 + 30.0 * k for k in range(9)), tuple((10 + 3 * k, "interf", 10 + k, -165.0 + 30.0 * k) for k in range(6)))])
+def test_lifted_shape_limits_match_oracle(algo, mics, hop, interf, events):
+    """Shapes round 1 refused: das with 8-16 microphones at 4096-point frames (microphones pass through shared memory in
+    chunks and accumulate, das.cpp:60-63 is linear), mvdr / lcmv with 8 microphones at 4096 points (spectra spill to a global
+    workspace), and up to the 15 interferers beamform_config.yaml:43-57 has slots for (general gated kernel)."""
+    cfg = bf.make_config(algo, mics=mics, hop=hop, initial_angle=10.0, interferers=interf)
+    n_hops = 31 if hop >= 1024 else 61
+    x = np.stack([synth_stream(bf.GEOMETRIES[mics], n_hops * hop, seed=900 + b) for b in range(2)])
+    o = Oracle(cfg)
+    ref0 = o.process(x[0], events=events)
+    ref = np.stack([ref0, Oracle(cfg).process(x[1], events=events)])
+    b = bf.Beamformer(cfg, n_streams=2)
+    got = b.process(x, events=events)
+    assert b.interferences == o.interferences
+    err = finite_rel_l2(got, ref)
+    print(algo, mics, "hop", hop, "interferers", len(o.interferences), "rel_l2", err)
+    assert err <= REL_L2_TOL
 
 
 # ---------------------------------------------------------------------------------------------
