@@ -42,8 +42,9 @@ cudaError_t launch_frames_kernel_mcra(const KernelParams& p, cudaStream_t st);
 cudaError_t launch_ref_kernel(const KernelParams& p, cudaStream_t st);
 cudaError_t launch_gsc(const KernelParams& p, cudaStream_t st);
 size_t gsc_align_smem(int N, int M);
-cudaError_t launch_srp(const KernelParams& p, float2* xs, const double* tau, const double* freqs_l, float* maps, int D, int n_hops,
+cudaError_t launch_srp(const KernelParams& p, unsigned char* xi, const double* tau, const double* freqs_l, float* maps, int D, int n_hops,
                        cudaStream_t st);
+size_t srp_workspace_bytes(long long F);
 }   // namespace bf
 
 typedef std::complex<double> cd;
@@ -107,7 +108,7 @@ struct bf_handle {
   float2* d_gss_w = nullptr;    // gss: [B][Lsel][C][M]
   float2* d_sel_ws = nullptr;   // general gated kernel: [B][M][N] spectra workspace when they do not fit shared memory
   // steered-response sweep workspace
-  float2* d_srp_xs = nullptr;
+  unsigned char* d_srp_xs = nullptr;   // operand images [514][frame tiles][bf16 hi | lo tile] (srp_kernel.cu)
   size_t srp_xs_cap = 0;
   double* d_srp_tau = nullptr;
   size_t srp_tau_cap = 0;
@@ -1007,12 +1008,14 @@ extern "C" int bf_srp_batch_device(bf_handle* h, const float* in_dev, size_t ss,
   CUDA_TRY(cudaSetDevice(h->dev));
   cudaStream_t st = (cudaStream_t)cuda_stream;
   const size_t F = (size_t)h->B * n_hops;
-  const size_t need_xs = (size_t)h->L * F * h->M;
+  const size_t need_xs = bf::srp_workspace_bytes((long long)F);
   if (need_xs > h->srp_xs_cap) {
     if (h->d_srp_xs) cudaFree(h->d_srp_xs);
     h->d_srp_xs = nullptr; h->srp_xs_cap = 0;
-    if (cudaMalloc(&h->d_srp_xs, sizeof(float2) * need_xs) != cudaSuccess) return fail(BF_ERR_ALLOC, "bf_srp_batch_device: spectra workspace");
+    if (cudaMalloc(&h->d_srp_xs, need_xs) != cudaSuccess) return fail(BF_ERR_ALLOC, "bf_srp_batch_device: spectra workspace");
     h->srp_xs_cap = need_xs;
+    // rows of frames beyond F, microphones beyond M and the layout padding are never written: they must read as zero
+    CUDA_TRY(cudaMemsetAsync(h->d_srp_xs, 0, need_xs, st));
   }
   const size_t need_tau = (size_t)n_dirs * h->M;
   if (need_tau > h->srp_tau_cap) {

@@ -16,6 +16,7 @@
 // No block-level barrier exists after start-up; spectra never leave the SM; every input hop is fetched from
 // HBM once (its second use, as "previous hop" of the next pair, hits L2) and every output sample is written once.
 // A range that starts inside a stream first recomputes the pair before it (no stores) to obtain the OLA tail.
+#include <cstdio>
 #include <cstdlib>
 
 #include "async_copy.cuh"
@@ -34,7 +35,8 @@ constexpr int kTileF2 = 1024;   // float2 per warp tile (8 KB, XOR-swizzled: no 
 // hot loop then fits the SM's instruction caches (a fully inlined forward+inverse pair was 85 KB of SASS and the
 // warps stalled on instruction fetch).  The inverse transform reuses this code through
 // IFFT(x) = swap(FFT(swap(x))), swap = exchange of real and imaginary parts (a register renaming).
-__device__ __forceinline__ void warp_fft1024_fwd(float2 (&v)[32], float2* tile, const float2* __restrict__ tw, int lane) {
+template <class F>
+__device__ __forceinline__ void warp_fft1024_fwd(float2 (&v)[32], float2* tile, const float2* __restrict__ tw, int lane, F&& after_exchange) {
 #pragma unroll 1
   for (int pass = 0; pass < 2; pass++) {
     fft_dit<32, -1>(v);
@@ -52,6 +54,7 @@ __device__ __forceinline__ void warp_fft1024_fwd(float2 (&v)[32], float2* tile, 
         v[brev5(2 * q + 1)] = make_float2(r.z, r.w);
       });
       __syncwarp();
+      after_exchange();   // the tile is free from here until the next job reads its staged hops
     }
   }
 }
@@ -62,13 +65,16 @@ struct PairPos {
   bool two;   // frame t+1 exists
 };
 
-template <int kWarps>
+// kTiles = 2: the next job's hops land in the second tile while the current job transforms (round 1).  kTiles = 1: they land in
+// the SAME tile as soon as the transform's exchange step has read it (behind the second FFT pass and the accumulation), which
+// halves the shared memory per warp so that 12 warps fit beside the weights: more warps hide more of the issue latency.
+template <int kWarps, int kTiles>
 __global__ void __launch_bounds__(kWarps * 32, 1) das_pairs_kernel(const KernelParams p, const int ceff_in_smem) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   float2* tw = reinterpret_cast<float2*>(smem_raw);                         // [32][32]
-  float2* tiles = tw + 1024;                                                  // [kWarps][2][1024]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(tiles + (size_t)kWarps * 2 * kTileF2);   // [kWarps][2]
-  float* tails = reinterpret_cast<float*>(bars + kWarps * 2);               // [kWarps][512] OLA tails
+  float2* tiles = tw + 1024;                                                  // [kWarps][kTiles][1024]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(tiles + (size_t)kWarps * kTiles * kTileF2);   // [kWarps][kTiles]
+  float* tails = reinterpret_cast<float*>(bars + kWarps * kTiles);          // [kWarps][512] OLA tails
   float2* ceff_s = reinterpret_cast<float2*>(tails + kWarps * 512);         // [M][1024] when it fits
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int M = p.M;
@@ -82,15 +88,13 @@ __global__ void __launch_bounds__(kWarps * 32, 1) das_pairs_kernel(const KernelP
   }
   if (ceff_in_smem)
     for (int i = tid; i < M * 1024; i += blockDim.x) ceff_s[i] = p.das_ceff[i];
-  if (lane == 0) {
-    mbar_init(&bars[warp * 2 + 0], 1);
-    mbar_init(&bars[warp * 2 + 1], 1);
-  }
+  if (lane == 0)
+    for (int b = 0; b < kTiles; b++) mbar_init(&bars[warp * kTiles + b], 1);
   mbar_fence_init();
   __syncthreads();
   const float2* ceff = ceff_in_smem ? ceff_s : p.das_ceff;
-  float2* mytile = tiles + (size_t)warp * 2 * kTileF2;
-  uint64_t* mybar = bars + warp * 2;
+  float2* mytile = tiles + (size_t)warp * kTiles * kTileF2;
+  uint64_t* mybar = bars + warp * kTiles;
 
   double sd, cd;
   sincospi((double)lane / 1024.0, &sd, &cd);
@@ -154,16 +158,19 @@ __global__ void __launch_bounds__(kWarps * 32, 1) das_pairs_kernel(const KernelP
       const bool fwd = ch < M;
       float2 v[32];
       float2* tile;
+      const PairPos pnext = make_pos(cur_sl, cur_q);
       if (fwd) {
-        const int b = job & 1;
-        // the other tile is free (its transform finished in the previous job): start the next stage-in
-        fence_proxy_async();
-        __syncwarp();
-        if (ch + 1 < M) issue(pp, ch + 1, b ^ 1);
-        else if (g + 1 < g_end) issue(make_pos(cur_sl, cur_q), 0, b ^ 1);
+        const int b = (kTiles == 2) ? (int)(job & 1) : 0;
+        if (kTiles == 2) {
+          // the other tile is free (its transform finished in the previous job): start the next stage-in
+          fence_proxy_async();
+          __syncwarp();
+          if (ch + 1 < M) issue(pp, ch + 1, b ^ 1);
+          else if (g + 1 < g_end) issue(pnext, 0, b ^ 1);
+        }
         tile = mytile + (size_t)b * kTileF2;
         const float* stg = reinterpret_cast<const float*>(tile);
-        mbar_wait(&mybar[b], (job >> 1) & 1);
+        mbar_wait(&mybar[b], (kTiles == 2) ? ((job >> 1) & 1) : (job & 1));
         static_for<0, 16>([&](auto r) {
           const float a = stg[32 * r + lane], bb = stg[512 + 32 * r + lane];
           const float c = pp.two ? stg[1024 + 32 * r + lane] : 0.0f;
@@ -176,11 +183,21 @@ __global__ void __launch_bounds__(kWarps * 32, 1) das_pairs_kernel(const KernelP
         job++;
       } else {
         // inverse straight from the accumulators (stage 1 wants g[32*n1 + lane] in slot brev5(n1)), parts swapped
-        tile = mytile + (size_t)((job - 1) & 1) * kTileF2;
+        tile = mytile + ((kTiles == 2) ? (size_t)((job - 1) & 1) * kTileF2 : 0);
         static_for<0, 32>([&](auto n1) { v[brev5(n1)] = make_float2(acc[n1].y, acc[n1].x); });
         __syncwarp();
       }
-      warp_fft1024_fwd(v, tile, tw, lane);
+      warp_fft1024_fwd(v, tile, tw, lane, [&]() {
+        if (kTiles == 1) {
+          // one tile: the next job's hops may land once this transform no longer needs the tile.  The job before the inverse
+          // issues nothing (the inverse exchanges through the tile too); the inverse issues the next pair's first microphone.
+          const bool nxt_mic = ch + 1 < M, nxt_pair = (ch == M) && (g + 1 < g_end);
+          if (nxt_mic || nxt_pair) {
+            fence_proxy_async();
+            if (nxt_mic) issue(pp, ch + 1, 0); else issue(pnext, 0, 0);
+          }
+        }
+      });
       if (fwd) {
         // das.cpp:60-63 on the packed spectrum: G[j] += ceff_i[j] * Z_i[j],  j = lane + 32*k2
         const float2* cw = ceff + (size_t)ch * 1024 + lane;
@@ -209,22 +226,18 @@ __global__ void __launch_bounds__(kWarps * 32, 1) das_pairs_kernel(const KernelP
   }
 }
 
-static int das_pick_warps(int M, int* ceff_in_smem, size_t* smem) {
+static int das_pick_warps(int M, int* ceff_in_smem, size_t* smem, int* tiles) {
   const size_t cap = 232448 - 1024;   // 227 KB dynamic limit, minus slack
   const size_t fixed = 1024 * sizeof(float2);
-  const size_t per_warp = 2 * kTileF2 * sizeof(float2) + 2 * sizeof(uint64_t) + 512 * sizeof(float);
   const size_t ceff = (size_t)M * 1024 * sizeof(float2);
-  int forced = 0;
-  if (const char* e = getenv("BF_DAS_WARPS")) forced = atoi(e);   // tuning knob: 8 or 12
-  int best = 0;
-  *ceff_in_smem = 0;
-  for (int wv : {8, 12}) {
-    if (forced && wv != forced) continue;
-    if (fixed + wv * per_warp + ceff <= cap) { best = wv; *ceff_in_smem = 1; break; }
-  }
-  if (!best) best = 8;   // large arrays: weights stay in global memory (L2-resident)
-  *smem = fixed + best * per_warp + (*ceff_in_smem ? ceff : 0);
-  return best;
+  int want_w = 12, want_t = 1;         // measured on B200 (profiles/): 12 warps x 1 tile beats 8 warps x 2 tiles
+  if (const char* e = getenv("BF_DAS_CFG")) sscanf(e, "%dx%d", &want_w, &want_t);   // tuning knob: 8x2, 8x1, 12x1
+  if (!((want_w == 8 || want_w == 12) && (want_t == 1 || want_t == 2)) || (want_w == 12 && want_t == 2)) { want_w = 12; want_t = 1; }
+  const size_t per_warp = (size_t)want_t * kTileF2 * sizeof(float2) + (size_t)want_t * sizeof(uint64_t) + 512 * sizeof(float);
+  *tiles = want_t;
+  *ceff_in_smem = (fixed + want_w * per_warp + ceff <= cap) ? 1 : 0;   // large arrays: weights stay in global memory (L2-resident)
+  *smem = fixed + want_w * per_warp + (*ceff_in_smem ? ceff : 0);
+  return want_w;
 }
 
 // true when the bulk-copy alignment rules hold (16-byte aligned base, strides multiples of 4 floats)
@@ -234,26 +247,27 @@ bool das_pairs_supported(const KernelParams& p) {
          (p.in_mic_stride & 3) == 0;
 }
 
-template <int kWarps>
+template <int kWarps, int kTiles>
 static cudaError_t launch_das_pairs_t(const KernelParams& p, cudaStream_t st, int ctas, size_t smem, int in_smem) {
-  cudaError_t e = cudaFuncSetAttribute(das_pairs_kernel<kWarps>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = cudaFuncSetAttribute(das_pairs_kernel<kWarps, kTiles>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  das_pairs_kernel<kWarps><<<ctas, kWarps * 32, smem, st>>>(p, in_smem);
+  das_pairs_kernel<kWarps, kTiles><<<ctas, kWarps * 32, smem, st>>>(p, in_smem);
   return cudaGetLastError();
 }
 
 // one CTA per SM
 cudaError_t launch_das_pairs(const KernelParams& p, cudaStream_t st, int sm_count) {
-  int in_smem = 0;
+  int in_smem = 0, tiles = 1;
   size_t smem = 0;
-  const int warps = das_pick_warps(p.M, &in_smem, &smem);
+  const int warps = das_pick_warps(p.M, &in_smem, &smem, &tiles);
   const int nh = p.hop_end - p.hop_begin;
   const long long total = (long long)p.n_streams * ((nh + 1) / 2);
   long long ctas = (total + warps - 1) / warps;
   if (ctas > sm_count) ctas = sm_count;
   if (ctas < 1) ctas = 1;
-  if (warps == 12) return launch_das_pairs_t<12>(p, st, (int)ctas, smem, in_smem);
-  return launch_das_pairs_t<8>(p, st, (int)ctas, smem, in_smem);
+  if (warps == 12) return launch_das_pairs_t<12, 1>(p, st, (int)ctas, smem, in_smem);
+  if (tiles == 1) return launch_das_pairs_t<8, 1>(p, st, (int)ctas, smem, in_smem);
+  return launch_das_pairs_t<8, 2>(p, st, (int)ctas, smem, in_smem);
 }
 
 }   // namespace bf

@@ -3,14 +3,15 @@
 // evaluated for D look directions per frame; map[s][t][d] = sum_{j=0}^{N-1} |y_d[j]|^2.
 //
 // Two kernels, 1024-point frames, M <= 64:
-//   srp_spectra_kernel  window -> packed FFT of every microphone of a frame pair (same warp-private transform as the
-//                       beamforming kernels) -> half spectra + pseudo-bin, written bin-major XS[l][frame][mic]
-//   srp_power_kernel    per bin l a complex GEMM  Y_l[d][f] = A_l[d][i] X_l[i][f]  (A_l generated on the fly from the
-//                       delay table, exact phase reduction in double), |Y|^2 weighted by the bin's multiplicity
-//                       (mirror bins share |y|, SURVEY B-3/B-4 pair excepted) and accumulated over l in registers.
-// The product path runs the contraction on tcgen05 (srp_tc_kernel.cu, BF16x3 split, TMEM accumulators); the FP32-pipe
-// version below (64x64x64 shared-memory tiles, 4x4 register tiles) is kept as an A/B cross-check (env BF_SRP_FP32).
+//   srp_spectra_kernel     window -> packed FFT of every microphone of a frame pair (same warp-private transform as the
+//                          beamforming kernels) -> half spectra + pseudo-bin, split into bf16 hi/lo and written as the
+//                          ready-made A-operand images of the tensor-core kernel
+//   srp_power_tc_kernel    (srp_tc_kernel.cu) per bin l a complex GEMM Y_l[f][d] = sum_i X_l[f][i] A_l[d][i] on tcgen05
+//                          (BF16x3 split, TMEM accumulators), |Y|^2 weighted by the bin's multiplicity (mirror bins share
+//                          |y|, SURVEY B-3/B-4 pair excepted) and accumulated over l in registers.
 #include <cstdlib>
+
+#include <cuda_bf16.h>
 
 #include "bf_device.h"
 #include "fft_reg.cuh"
@@ -43,8 +44,8 @@ __device__ __forceinline__ void srp_fft1024_fwd(float2 (&v)[32], float2* tile, c
   }
 }
 
-// grid = (pairs, streams); XS[l][f][i], f = s*n_hops + t
-__global__ void __launch_bounds__(256, 1) srp_spectra_kernel(const KernelParams p, float2* __restrict__ xs, int n_hops) {
+// grid = (pairs, streams); frame index f = s*n_hops + t
+__global__ void __launch_bounds__(256, 1) srp_spectra_kernel(const KernelParams p, unsigned char* __restrict__ xi, int n_hops, size_t image_bytes, size_t lbo) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   float2* tw = reinterpret_cast<float2*>(smem_raw);
   float2* tiles = tw + 1024;
@@ -67,6 +68,7 @@ __global__ void __launch_bounds__(256, 1) srp_spectra_kernel(const KernelParams 
   // transposing read below (eight lanes = eight microphones at the same bin) is conflict-free
   float2* tile = tiles + (size_t)warp * kSrpTilePitch;
   const size_t F = (size_t)p.n_streams * n_hops;
+  const size_t n_ft = (F + 127) / 128;
   const size_t f0 = (size_t)s * n_hops + t;
   for (int r0 = 0; r0 < M; r0 += 8) {
     const int ch = r0 + warp;
@@ -89,20 +91,41 @@ __global__ void __launch_bounds__(256, 1) srp_spectra_kernel(const KernelParams 
       for (int k2 = 0; k2 < 32; k2++) tile[k2 * 32 + lane] = v[k2];
     }
     __syncthreads();
-    // The eight spectra of the round leave together: lanes 8q..8q+7 carry the eight microphones of one bin, so every
-    // (bin, frame) gets one 64-byte run of XS[l][f][r0..r0+7] (full sectors) instead of eight scattered 8-byte stores.
-    {
-      const int m = tid & 7;
-      if (r0 + m < M) {
-        const float2* zt = tiles + (size_t)m * kSrpTilePitch;
-        for (int l = tid >> 3; l < kSrpL; l += 32) {
-          const int j = (l == kSrpL - 1) ? 511 : l;
+    // Output: the A-operand IMAGES of the tensor-core kernel (srp_tc_kernel.cu): per (bin, tile of 128 frames) a bf16 hi
+    // tile and a bf16 lo tile in the UMMA core-matrix layout, element (frame row, k) with k = microphone (real parts) and
+    // 64 + microphone (imaginary parts).  The eight microphones of a round are one 16-byte core-matrix row, the two frames
+    // of the pair are neighbouring rows: each thread (one bin) writes full 16-byte pieces, frame pairs fill 32-byte sectors.
+    for (int l = tid; l < kSrpL; l += 256) {
+      const int j = (l == kSrpL - 1) ? 511 : l;
+      __align__(16) __nv_bfloat16 h[2][2][8];    // [frame][re/im][microphone of the round]
+      __align__(16) __nv_bfloat16 lo[2][2][8];
+#pragma unroll
+      for (int m = 0; m < 8; m++) {
+        float x[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
+        if (r0 + m < M) {
+          const float2* zt = tiles + (size_t)m * kSrpTilePitch;
           const float2 a = zt[j], b = zt[(1024 - j) & 1023];
-          float2 x0 = make_float2(a.x + b.x, a.y - b.y);
-          float2 x1 = make_float2(a.y + b.y, b.x - a.x);
-          if (l == kSrpL - 1) { x0.y = -x0.y; x1.y = -x1.y; }   // pseudo-bin: conj of bin N/2-1 (SURVEY B-4)
-          xs[((size_t)l * F + f0) * M + r0 + m] = x0;
-          if (two) xs[((size_t)l * F + f0 + 1) * M + r0 + m] = x1;
+          x[0][0] = a.x + b.x; x[0][1] = a.y - b.y;
+          x[1][0] = a.y + b.y; x[1][1] = b.x - a.x;
+          if (l == kSrpL - 1) { x[0][1] = -x[0][1]; x[1][1] = -x[1][1]; }   // pseudo-bin: conj of bin N/2-1 (SURVEY B-4)
+        }
+#pragma unroll
+        for (int f = 0; f < 2; f++)
+#pragma unroll
+          for (int c = 0; c < 2; c++) {
+            h[f][c][m] = __float2bfloat16_rn(x[f][c]);
+            lo[f][c][m] = __float2bfloat16_rn(x[f][c] - __bfloat162float(h[f][c][m]));
+          }
+      }
+      for (int f = 0; f < (two ? 2 : 1); f++) {
+        const size_t fr = f0 + f;
+        unsigned char* img = xi + ((size_t)l * n_ft + (fr >> 7)) * image_bytes;
+        const int row = (int)(fr & 127);
+#pragma unroll
+        for (int c = 0; c < 2; c++) {
+          const size_t off = (size_t)((c * 64 + r0) >> 3) * lbo + (size_t)(row >> 3) * 128 + (size_t)(row & 7) * 16;
+          *reinterpret_cast<uint4*>(img + off) = *reinterpret_cast<const uint4*>(h[f][c]);
+          *reinterpret_cast<uint4*>(img + image_bytes / 2 + off) = *reinterpret_cast<const uint4*>(lo[f][c]);
         }
       }
     }
@@ -110,109 +133,25 @@ __global__ void __launch_bounds__(256, 1) srp_spectra_kernel(const KernelParams 
   }
 }
 
-constexpr int kTD = 64, kTF = 64;   // CTA tile: directions x frames
-constexpr int kPad = 65;            // float2 row pitch of the shared tiles (odd: conflict-free column reads)
-
-// grid = (ceil(F/64), ceil(D/64)); maps[f][d]
-__global__ void __launch_bounds__(256, 2) srp_power_kernel(const float2* __restrict__ xs, const double* __restrict__ tau /*[D][M]*/,
-                                                            const double* __restrict__ freqs_l /*[514]*/, float* __restrict__ maps, int D, int M,
-                                                            long long F) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  float2* As = reinterpret_cast<float2*>(smem_raw);   // [64 i][65]: As[i][d]
-  float2* Xs = As + 64 * kPad;                         // [64 i][65]: Xs[i][f]
-  const int tid = threadIdx.x;
-  const int td = tid & 15, tf = tid >> 4;              // 16 x 16 threads, each a 4 (d) x 4 (f) register tile
-  const long long fbase = (long long)blockIdx.x * kTF;
-  const int dbase = blockIdx.y * kTD;
-  float pw[4][4];
-#pragma unroll
-  for (int a = 0; a < 4; a++)
-#pragma unroll
-    for (int b = 0; b < 4; b++) pw[a][b] = 0.f;
-  const float invM = 1.0f / (float)M;
-
-  for (int l = 0; l < kSrpL; l++) {
-    const double fl = freqs_l[l];
-    float2 acc[4][4];
-#pragma unroll
-    for (int a = 0; a < 4; a++)
-#pragma unroll
-      for (int b = 0; b < 4; b++) acc[a][b] = make_float2(0.f, 0.f);
-    for (int i0 = 0; i0 < M; i0 += 64) {
-      __syncthreads();
-      // A_l[d][i] = exp(+i 2 pi f_l tau_{d,i}) / M  (conj of das.cpp:41), phase reduced to one turn in double
-      for (int e = tid; e < 64 * 64; e += 256) {
-        const int d = e >> 6, i = e & 63;
-        float2 val = make_float2(0.f, 0.f);
-        if (dbase + d < D && i0 + i < M) {
-          const double turns = fl * tau[(size_t)(dbase + d) * M + i0 + i];
-          const float fr = (float)(turns - rint(turns));
-          float sn, cs;
-          sincospif(2.0f * fr, &sn, &cs);
-          val = make_float2(cs * invM, sn * invM);
-        }
-        As[i * kPad + d] = val;
-      }
-      for (int e = tid; e < 64 * 64; e += 256) {
-        const int f = e >> 6, i = e & 63;
-        float2 val = make_float2(0.f, 0.f);
-        if (fbase + f < F && i0 + i < M) val = xs[((size_t)l * F + fbase + f) * M + i0 + i];
-        Xs[i * kPad + f] = val;
-      }
-      __syncthreads();
-#pragma unroll 4
-      for (int i = 0; i < 64; i++) {
-        float2 av[4], xv[4];
-#pragma unroll
-        for (int a = 0; a < 4; a++) av[a] = As[i * kPad + td + 16 * a];
-#pragma unroll
-        for (int b = 0; b < 4; b++) xv[b] = Xs[i * kPad + tf + 16 * b];
-#pragma unroll
-        for (int a = 0; a < 4; a++)
-#pragma unroll
-          for (int b = 0; b < 4; b++) {
-            acc[a][b].x = fmaf(av[a].x, xv[b].x, acc[a][b].x); acc[a][b].x = fmaf(-av[a].y, xv[b].y, acc[a][b].x);
-            acc[a][b].y = fmaf(av[a].x, xv[b].y, acc[a][b].y); acc[a][b].y = fmaf(av[a].y, xv[b].x, acc[a][b].y);
-          }
-      }
-    }
-    // bins 1..N/2-2 stand for themselves and their mirrors (|y[N-j]| = |y[j]|); 0, N/2-1, N/2 and the pseudo-bin count once
-    const float wgt = (l == 0 || l >= 511) ? 1.0f : 2.0f;
-#pragma unroll
-    for (int a = 0; a < 4; a++)
-#pragma unroll
-      for (int b = 0; b < 4; b++) pw[a][b] = fmaf(wgt, fmaf(acc[a][b].x, acc[a][b].x, acc[a][b].y * acc[a][b].y), pw[a][b]);
-  }
-#pragma unroll
-  for (int a = 0; a < 4; a++)
-#pragma unroll
-    for (int b = 0; b < 4; b++) {
-      const int d = dbase + td + 16 * a;
-      const long long f = fbase + tf + 16 * b;
-      if (d < D && f < F) maps[(size_t)f * D + d] = pw[a][b];
-    }
-}
-
-cudaError_t launch_srp_power_tc(const float2* xs, const double* tau, const double* freqs_l, float* maps, int D, int M, long long F,
+cudaError_t launch_srp_power_tc(const unsigned char* xi, const double* tau, const double* freqs_l, float* maps, int D, int M, long long F,
                                 cudaStream_t st);
+size_t srp_image_bytes();
 
-cudaError_t launch_srp(const KernelParams& p, float2* xs, const double* tau, const double* freqs_l, float* maps, int D, int n_hops,
+// bytes of the operand-image workspace for F frames: [514 bins][ceil(F/128) frame tiles][image]
+size_t srp_workspace_bytes(long long F) { return (size_t)kSrpL * (size_t)((F + 127) / 128) * srp_image_bytes(); }
+
+cudaError_t launch_srp(const KernelParams& p, unsigned char* xi, const double* tau, const double* freqs_l, float* maps, int D, int n_hops,
                        cudaStream_t st) {
   const size_t smem1 = sizeof(float2) * (1024 + 8 * kSrpTilePitch);
   cudaError_t e = cudaFuncSetAttribute(srp_spectra_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1);
   if (e != cudaSuccess) return e;
   dim3 g1((n_hops + 1) / 2, p.n_streams);
-  srp_spectra_kernel<<<g1, 256, smem1, st>>>(p, xs, n_hops);
+  const size_t image = srp_image_bytes(), lbo = image / 2 / 16;   // 16 K-cores per tile
+  srp_spectra_kernel<<<g1, 256, smem1, st>>>(p, xi, n_hops, image, lbo);
   e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   const long long F = (long long)p.n_streams * n_hops;
-  if (!getenv("BF_SRP_FP32")) return launch_srp_power_tc(xs, tau, freqs_l, maps, D, p.M, F, st);   // tensor-core path (default)
-  const size_t smem2 = sizeof(float2) * 2 * 64 * kPad;
-  e = cudaFuncSetAttribute(srp_power_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
-  if (e != cudaSuccess) return e;
-  dim3 g2((unsigned)((F + kTF - 1) / kTF), (unsigned)((D + kTD - 1) / kTD));
-  srp_power_kernel<<<g2, 256, smem2, st>>>(xs, tau, freqs_l, maps, D, p.M, F);
-  return cudaGetLastError();
+  return launch_srp_power_tc(xi, tau, freqs_l, maps, D, p.M, F, st);
 }
 
 }   // namespace bf
