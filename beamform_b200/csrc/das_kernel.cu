@@ -67,7 +67,8 @@ struct PairPos {
 
 // kTiles = 2: the next job's hops land in the second tile while the current job transforms (round 1).  kTiles = 1: they land in
 // the SAME tile as soon as the transform's exchange step has read it (behind the second FFT pass and the accumulation), which
-// halves the shared memory per warp so that 12 warps fit beside the weights: more warps hide more of the issue latency.
+// halves the shared memory per warp (12 warps fit beside the weights; measured slower: the kernel is bound by the issue rate of
+// the butterflies, not by latency, and 12 warps leave 168 registers per thread).
 template <int kWarps, int kTiles>
 __global__ void __launch_bounds__(kWarps * 32, 1) das_pairs_kernel(const KernelParams p, const int ceff_in_smem) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -230,9 +231,9 @@ static int das_pick_warps(int M, int* ceff_in_smem, size_t* smem, int* tiles) {
   const size_t cap = 232448 - 1024;   // 227 KB dynamic limit, minus slack
   const size_t fixed = 1024 * sizeof(float2);
   const size_t ceff = (size_t)M * 1024 * sizeof(float2);
-  int want_w = 12, want_t = 1;         // measured on B200 (profiles/): 12 warps x 1 tile beats 8 warps x 2 tiles
+  int want_w = 8, want_t = 1;          // measured on B200 (C1, audio-s/s): 8x2 2.597 M, 8x1 2.605 M, 12x1 2.229 M (168 registers, spills)
   if (const char* e = getenv("BF_DAS_CFG")) sscanf(e, "%dx%d", &want_w, &want_t);   // tuning knob: 8x2, 8x1, 12x1
-  if (!((want_w == 8 || want_w == 12) && (want_t == 1 || want_t == 2)) || (want_w == 12 && want_t == 2)) { want_w = 12; want_t = 1; }
+  if (!((want_w == 8 || want_w == 12) && (want_t == 1 || want_t == 2)) || (want_w == 12 && want_t == 2)) { want_w = 8; want_t = 1; }
   const size_t per_warp = (size_t)want_t * kTileF2 * sizeof(float2) + (size_t)want_t * sizeof(uint64_t) + 512 * sizeof(float);
   *tiles = want_t;
   *ceff_in_smem = (fixed + want_w * per_warp + ceff <= cap) ? 1 : 0;   // large arrays: weights stay in global memory (L2-resident)

@@ -95,37 +95,37 @@ __global__ void __launch_bounds__(256, 1) srp_spectra_kernel(const KernelParams 
     // tile and a bf16 lo tile in the UMMA core-matrix layout, element (frame row, k) with k = microphone (real parts) and
     // 64 + microphone (imaginary parts).  The eight microphones of a round are one 16-byte core-matrix row, the two frames
     // of the pair are neighbouring rows: each thread (one bin) writes full 16-byte pieces, frame pairs fill 32-byte sectors.
-    for (int l = tid; l < kSrpL; l += 256) {
+    // A lane PAIR per bin: lane parity = frame of the pair, so the two 16-byte pieces of a store instruction's neighbouring
+    // lanes are the two neighbouring rows of one 32-byte sector.
+    for (int it = tid; it < 2 * kSrpL; it += 256) {
+      const int l = it >> 1, f = it & 1;
       const int j = (l == kSrpL - 1) ? 511 : l;
-      __align__(16) __nv_bfloat16 h[2][2][8];    // [frame][re/im][microphone of the round]
-      __align__(16) __nv_bfloat16 lo[2][2][8];
+      __align__(16) __nv_bfloat16 h[2][8];    // [re/im][microphone of the round]
+      __align__(16) __nv_bfloat16 lo[2][8];
 #pragma unroll
       for (int m = 0; m < 8; m++) {
-        float x[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
+        float xr = 0.f, xim = 0.f;
         if (r0 + m < M) {
           const float2* zt = tiles + (size_t)m * kSrpTilePitch;
           const float2 a = zt[j], b = zt[(1024 - j) & 1023];
-          x[0][0] = a.x + b.x; x[0][1] = a.y - b.y;
-          x[1][0] = a.y + b.y; x[1][1] = b.x - a.x;
-          if (l == kSrpL - 1) { x[0][1] = -x[0][1]; x[1][1] = -x[1][1]; }   // pseudo-bin: conj of bin N/2-1 (SURVEY B-4)
+          xr = f ? a.y + b.y : a.x + b.x;
+          xim = f ? b.x - a.x : a.y - b.y;
+          if (l == kSrpL - 1) xim = -xim;   // pseudo-bin: conj of bin N/2-1 (SURVEY B-4)
         }
-#pragma unroll
-        for (int f = 0; f < 2; f++)
-#pragma unroll
-          for (int c = 0; c < 2; c++) {
-            h[f][c][m] = __float2bfloat16_rn(x[f][c]);
-            lo[f][c][m] = __float2bfloat16_rn(x[f][c] - __bfloat162float(h[f][c][m]));
-          }
+        h[0][m] = __float2bfloat16_rn(xr);
+        lo[0][m] = __float2bfloat16_rn(xr - __bfloat162float(h[0][m]));
+        h[1][m] = __float2bfloat16_rn(xim);
+        lo[1][m] = __float2bfloat16_rn(xim - __bfloat162float(h[1][m]));
       }
-      for (int f = 0; f < (two ? 2 : 1); f++) {
+      if (f == 0 || two) {
         const size_t fr = f0 + f;
         unsigned char* img = xi + ((size_t)l * n_ft + (fr >> 7)) * image_bytes;
         const int row = (int)(fr & 127);
 #pragma unroll
         for (int c = 0; c < 2; c++) {
           const size_t off = (size_t)((c * 64 + r0) >> 3) * lbo + (size_t)(row >> 3) * 128 + (size_t)(row & 7) * 16;
-          *reinterpret_cast<uint4*>(img + off) = *reinterpret_cast<const uint4*>(h[f][c]);
-          *reinterpret_cast<uint4*>(img + image_bytes / 2 + off) = *reinterpret_cast<const uint4*>(lo[f][c]);
+          *reinterpret_cast<uint4*>(img + off) = *reinterpret_cast<const uint4*>(h[c]);
+          *reinterpret_cast<uint4*>(img + image_bytes / 2 + off) = *reinterpret_cast<const uint4*>(lo[c]);
         }
       }
     }
