@@ -22,6 +22,7 @@
 #include "async_copy.cuh"
 #include "bf_device.h"
 #include "fft_reg.cuh"
+#include "tmem.cuh"
 #include "warp_fft1024.cuh"
 
 namespace bf {
@@ -69,7 +70,10 @@ struct PairPos {
 // the SAME tile as soon as the transform's exchange step has read it (behind the second FFT pass and the accumulation), which
 // halves the shared memory per warp (12 warps fit beside the weights; measured slower: the kernel is bound by the issue rate of
 // the butterflies, not by latency, and 12 warps leave 168 registers per thread).
-template <int kWarps, int kTiles>
+// kTmem: the per-pair accumulator G (32 complex values per lane) lives in tensor memory instead of registers (tcgen05.ld / st,
+// 64 columns per warp in its lane quarter): the kernel then fits 128 registers per thread and SIXTEEN warps per SM, which fill
+// the issue slots two warps per scheduler leave empty (round 1: 64 % issue utilisation, stalls "wait" and "short scoreboard").
+template <int kWarps, int kTiles, bool kTmem>
 __global__ void __launch_bounds__(kWarps * 32, 1) das_pairs_kernel(const KernelParams p, const int ceff_in_smem) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   float2* tw = reinterpret_cast<float2*>(smem_raw);                         // [32][32]
@@ -77,6 +81,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) das_pairs_kernel(const KernelP
   uint64_t* bars = reinterpret_cast<uint64_t*>(tiles + (size_t)kWarps * kTiles * kTileF2);   // [kWarps][kTiles]
   float* tails = reinterpret_cast<float*>(bars + kWarps * kTiles);          // [kWarps][512] OLA tails
   float2* ceff_s = reinterpret_cast<float2*>(tails + kWarps * 512);         // [M][1024] when it fits
+  __shared__ uint32_t tmem_slot;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int M = p.M;
   constexpr int H = 512;
@@ -92,7 +97,14 @@ __global__ void __launch_bounds__(kWarps * 32, 1) das_pairs_kernel(const KernelP
   if (lane == 0)
     for (int b = 0; b < kTiles; b++) mbar_init(&bars[warp * kTiles + b], 1);
   mbar_fence_init();
+  if (kTmem && warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "n"(256) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (kTmem) asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
+  if (kTmem) asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tacc = kTmem ? tmem_slot + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((warp >> 2) * 64) : 0u;   // this warp's 64 columns
   const float2* ceff = ceff_in_smem ? ceff_s : p.das_ceff;
   float2* mytile = tiles + (size_t)warp * kTiles * kTileF2;
   uint64_t* mybar = bars + warp * kTiles;
@@ -108,7 +120,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) das_pairs_kernel(const KernelP
   const long long total = (long long)p.n_streams * Tp;
   const long long W = (long long)gridDim.x * kWarps, w = (long long)blockIdx.x * kWarps + warp;
   const long long g_begin = total * w / W, g_end = total * (w + 1) / W;
-  if (g_begin >= g_end) return;
+  if (g_begin < g_end) {
   const bool warm = (g_begin % Tp) != 0;
   const long long g_first = warm ? g_begin - 1 : g_begin;
 
@@ -149,9 +161,11 @@ __global__ void __launch_bounds__(kWarps * 32, 1) das_pairs_kernel(const KernelP
       for (int m2 = 0; m2 < 16; m2++) mytail[32 * m2 + lane] = p.tail[(size_t)pp.s * H + 32 * m2 + lane];
     }
     const bool last = pp.t + 2 >= p.hop_end;   // stream end: persist the tail as state for the next call
-    float2 acc[32];
+    float2 acc[kTmem ? 1 : 32];
+    if (!kTmem) {
 #pragma unroll
-    for (int k = 0; k < 32; k++) acc[k] = make_float2(0.f, 0.f);
+      for (int k = 0; k < (kTmem ? 1 : 32); k++) acc[k] = make_float2(0.f, 0.f);
+    }
 
     // M forward jobs and one inverse job run through the same transform code (ch == M: inverse)
 #pragma unroll 1
@@ -185,7 +199,16 @@ __global__ void __launch_bounds__(kWarps * 32, 1) das_pairs_kernel(const KernelP
       } else {
         // inverse straight from the accumulators (stage 1 wants g[32*n1 + lane] in slot brev5(n1)), parts swapped
         tile = mytile + ((kTiles == 2) ? (size_t)((job - 1) & 1) * kTileF2 : 0);
-        static_for<0, 32>([&](auto n1) { v[brev5(n1)] = make_float2(acc[n1].y, acc[n1].x); });
+        if constexpr (kTmem) {
+          static_for<0, 4>([&](auto cc) {
+            uint32_t r[16];
+            tmem_ld16(tacc + 16u * cc, r);
+            tmem_wait_ld();
+            static_for<0, 8>([&](auto u) { v[brev5(8 * cc + u)] = make_float2(__uint_as_float(r[2 * u + 1]), __uint_as_float(r[2 * u])); });
+          });
+        } else {
+          static_for<0, 32>([&](auto n1) { v[brev5(n1)] = make_float2(acc[kTmem ? 0 : (int)n1].y, acc[kTmem ? 0 : (int)n1].x); });
+        }
         __syncwarp();
       }
       warp_fft1024_fwd(v, tile, tw, lane, [&]() {
@@ -202,11 +225,34 @@ __global__ void __launch_bounds__(kWarps * 32, 1) das_pairs_kernel(const KernelP
       if (fwd) {
         // das.cpp:60-63 on the packed spectrum: G[j] += ceff_i[j] * Z_i[j],  j = lane + 32*k2
         const float2* cw = ceff + (size_t)ch * 1024 + lane;
+        if constexpr (kTmem) {
+          static_for<0, 4>([&](auto cc) {   // 8 bins (16 columns) at a time: load the running sums, accumulate, store back
+            uint32_t r[16];
+            if (ch > 0) {
+              tmem_ld16(tacc + 16u * cc, r);
+              tmem_wait_ld();
+            } else {
 #pragma unroll
-        for (int k2 = 0; k2 < 32; k2++) {
-          const float2 c = cw[32 * k2];
-          acc[k2].x = fmaf(v[k2].x, c.x, acc[k2].x); acc[k2].x = fmaf(-v[k2].y, c.y, acc[k2].x);
-          acc[k2].y = fmaf(v[k2].x, c.y, acc[k2].y); acc[k2].y = fmaf(v[k2].y, c.x, acc[k2].y);
+              for (int u = 0; u < 16; u++) r[u] = 0u;
+            }
+            static_for<0, 8>([&](auto u) {
+              constexpr int k2 = 8 * cc + u;
+              const float2 c = cw[32 * k2];
+              float ax = __uint_as_float(r[2 * u]), ay = __uint_as_float(r[2 * u + 1]);
+              ax = fmaf(v[k2].x, c.x, ax); ax = fmaf(-v[k2].y, c.y, ax);
+              ay = fmaf(v[k2].x, c.y, ay); ay = fmaf(v[k2].y, c.x, ay);
+              r[2 * u] = __float_as_uint(ax); r[2 * u + 1] = __float_as_uint(ay);
+            });
+            tmem_st16(tacc + 16u * cc, r);
+          });
+          tmem_wait_st();
+        } else {
+#pragma unroll
+          for (int k2 = 0; k2 < (kTmem ? 0 : 32); k2++) {
+            const float2 c = cw[32 * k2];
+            acc[k2].x = fmaf(v[k2].x, c.x, acc[k2].x); acc[k2].x = fmaf(-v[k2].y, c.y, acc[k2].x);
+            acc[k2].y = fmaf(v[k2].x, c.y, acc[k2].y); acc[k2].y = fmaf(v[k2].y, c.x, acc[k2].y);
+          }
         }
       } else {
         // v = swap(IFFT(G)): frame t in .y, frame t+1 in .x; synthesis window + overlap-add (util.h:244-253,301-302)
@@ -225,15 +271,23 @@ __global__ void __launch_bounds__(kWarps * 32, 1) das_pairs_kernel(const KernelP
       }
     }
   }
+  }   // g_begin < g_end
+  if (kTmem) {
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_slot), "n"(256) : "memory");
+  }
 }
 
 static int das_pick_warps(int M, int* ceff_in_smem, size_t* smem, int* tiles) {
   const size_t cap = 232448 - 1024;   // 227 KB dynamic limit, minus slack
   const size_t fixed = 1024 * sizeof(float2);
   const size_t ceff = (size_t)M * 1024 * sizeof(float2);
-  int want_w = 8, want_t = 1;          // measured on B200 (C1, audio-s/s): 8x2 2.597 M, 8x1 2.605 M, 12x1 2.229 M (168 registers, spills)
-  if (const char* e = getenv("BF_DAS_CFG")) sscanf(e, "%dx%d", &want_w, &want_t);   // tuning knob: 8x2, 8x1, 12x1
-  if (!((want_w == 8 || want_w == 12) && (want_t == 1 || want_t == 2)) || (want_w == 12 && want_t == 2)) { want_w = 8; want_t = 1; }
+  // measured on B200 (C1, audio-s/s): 8x2 2.597 M, 8x1 2.605 M, 12x1 2.229 M (168 registers, spills), 16x1 with the accumulators
+  // in tensor memory 2.373 M (128 registers): the kernel is bound by the issue rate of the butterflies, more warps do not help
+  int want_w = 8, want_t = 1;
+  if (const char* e = getenv("BF_DAS_CFG")) sscanf(e, "%dx%d", &want_w, &want_t);   // tuning knob: 8x2, 8x1, 12x1, 16x1 (16 warps: accumulators in tensor memory)
+  if (!((want_w == 8 || want_w == 12 || want_w == 16) && (want_t == 1 || want_t == 2)) || (want_w > 8 && want_t == 2)) { want_w = 8; want_t = 1; }
   const size_t per_warp = (size_t)want_t * kTileF2 * sizeof(float2) + (size_t)want_t * sizeof(uint64_t) + 512 * sizeof(float);
   *tiles = want_t;
   *ceff_in_smem = (fixed + want_w * per_warp + ceff <= cap) ? 1 : 0;   // large arrays: weights stay in global memory (L2-resident)
@@ -248,11 +302,11 @@ bool das_pairs_supported(const KernelParams& p) {
          (p.in_mic_stride & 3) == 0;
 }
 
-template <int kWarps, int kTiles>
+template <int kWarps, int kTiles, bool kTmem>
 static cudaError_t launch_das_pairs_t(const KernelParams& p, cudaStream_t st, int ctas, size_t smem, int in_smem) {
-  cudaError_t e = cudaFuncSetAttribute(das_pairs_kernel<kWarps, kTiles>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = cudaFuncSetAttribute(das_pairs_kernel<kWarps, kTiles, kTmem>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  das_pairs_kernel<kWarps, kTiles><<<ctas, kWarps * 32, smem, st>>>(p, in_smem);
+  das_pairs_kernel<kWarps, kTiles, kTmem><<<ctas, kWarps * 32, smem, st>>>(p, in_smem);
   return cudaGetLastError();
 }
 
@@ -266,9 +320,10 @@ cudaError_t launch_das_pairs(const KernelParams& p, cudaStream_t st, int sm_coun
   long long ctas = (total + warps - 1) / warps;
   if (ctas > sm_count) ctas = sm_count;
   if (ctas < 1) ctas = 1;
-  if (warps == 12) return launch_das_pairs_t<12, 1>(p, st, (int)ctas, smem, in_smem);
-  if (tiles == 1) return launch_das_pairs_t<8, 1>(p, st, (int)ctas, smem, in_smem);
-  return launch_das_pairs_t<8, 2>(p, st, (int)ctas, smem, in_smem);
+  if (warps == 16) return launch_das_pairs_t<16, 1, true>(p, st, (int)ctas, smem, in_smem);
+  if (warps == 12) return launch_das_pairs_t<12, 1, false>(p, st, (int)ctas, smem, in_smem);
+  if (tiles == 1) return launch_das_pairs_t<8, 1, false>(p, st, (int)ctas, smem, in_smem);
+  return launch_das_pairs_t<8, 2, false>(p, st, (int)ctas, smem, in_smem);
 }
 
 }   // namespace bf

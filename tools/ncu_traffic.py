@@ -17,7 +17,7 @@ iID = hdr.index("ID")
 scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "ns": 1e-9, "us": 1e-6, "ms": 1e-3, "s": 1.0, "usecond": 1e-6, "msecond": 1e-3, "nsecond": 1e-9, "second": 1.0}
 per = defaultdict(dict)
 for r in rows[1:]:
-    if not any(k in r[iK] for k in ("bf::", "das_pairs_kernel", "sel_pairs_kernel", "frames_kernel", "srp_", "save_prev_hop", "gss_reset", "zero_hops", "ref_kernel", "gsc_")):
+    if not any(k in r[iK] for k in ("bf::", "das_pairs_kernel", "sel_pairs_kernel", "sel_stream_kernel", "frames_kernel", "srp_", "save_prev_hop", "gss_reset", "zero_hops", "ref_kernel", "gsc_")):
         continue
     per[(r[iID], r[iK])][r[iM]] = float(r[iV].replace(",", "")) * scale.get(r[iU], 1.0)
 agg = defaultdict(lambda: [0, 0.0, 0.0, 0.0])
@@ -33,6 +33,8 @@ k, a = max(agg.items(), key=lambda kv: kv[1][1])
 out = {"workload": wl, "kernel": k, "launches": a[0], "dram_bytes_read_per_launch": a[2] / a[0], "dram_bytes_write_per_launch": a[3] / a[0],
        "dram_bytes_per_launch": (a[2] + a[3]) / a[0], "ncu_time_ms_per_launch": 1e3 * a[1] / a[0],
        "share_of_bf_kernel_time": a[1] / sum(v[1] for v in agg.values()),
+       "dram_bytes_all_kernels_per_step": sum(v[2] + v[3] for v in agg.values()) / a[0],
+       "kernels": {kk: {"launches": v[0], "ms_per_launch": 1e3 * v[1] / v[0], "dram_bytes_per_launch": (v[2] + v[3]) / v[0]} for kk, v in agg.items()},
        "source": "ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none (bench shape)"}
 json.dump(out, open(os.path.join(out_dir, "traffic_%s.json" % wl), "w"), indent=1)
 print(json.dumps(out))
