@@ -1,4 +1,4 @@
-// Pipelined kernel for mvdr (the covariance node of BASELINE config C2), 1024-point frames, M <= 8, P <= 10, sm_100a.
+// Pipelined kernel for mvdr (BASELINE config C2), 1024-point frames, M <= 8, P <= 10, sm_100a.
 //
 //   reference path replaced (citations /root/reference/beamform/src/): util.h:217-253,289-314 (window, framing,
 //   OLA) and apply_weights of mvdr.cpp:62-115, lcmv.cpp:88-140 (history matrices past_ffts of mvdr.cpp:228-243).
@@ -146,6 +146,29 @@ __device__ __noinline__ bool ss_gate_fp64(const KernelParams& p, int s, int t, i
 // One solver batch: lanes 0-15 carry frame t of items 0-15, lanes 16-31 frame t+1.  Staged entries are ring slots
 // sigma = frame % Dt (Dt = P + 1): slot sx holds X_t, slot (sx + 1) % Dt holds X_{t-P}; the other P-1 slots are the frames
 // both histories contain (mvdr.cpp:87, :239-243: R_t over t-P..t-1, R_{t+1} over t-P+1..t).
+// gss (gss.cpp:118-137): one lane per staged bin runs the frames of the pair in order (the separation matrix W of the bin is a
+// recursion over the selected frames; it lives in global memory, L2-resident, bin index fastest).  Staged entries 0 / 1 = X_t / X_{t+1}.
+__device__ __noinline__ void ss_solve_batch_gss(const KernelParams& p, SsShared& sh, const SsBatch& bt, int lane, int s) {
+  if (lane >= bt.n_items || lane >= kSsItems) return;
+  const int l = bt.bin[lane];
+  float2* Wg = p.gss_w + (size_t)s * BF_GSS_ROWS * p.M * p.Lsel + sh.sel_slot[l];
+  const float2* steer_l = p.steer + (size_t)l * p.C * p.M;
+  const float4* it = reinterpret_cast<const float4*>(&bt.item[lane][0]);
+  for (int f = 0; f < 2; f++) {
+    if (!((bt.flags[lane] >> f) & 1)) continue;
+    float2 x[8];
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      const float4 r = it[f * 4 + q];
+      x[2 * q] = make_float2(r.x, r.y);
+      x[2 * q + 1] = make_float2(r.z, r.w);
+    }
+    const float2 yv = gss_item(p, Wg, (size_t)p.Lsel, x, steer_l);
+    sh.y[bt.ybuf][f][l] = yv;
+    if (!(isfinite(yv.x) && isfinite(yv.y))) sh.nonfinite[bt.ybuf][f] = 1;
+  }
+}
+
 template <int ALGO>
 __device__ __noinline__ void ss_solve_batch(const KernelParams& p, SsShared& sh, const SsBatch& bt, int lane) {
   typedef typename std::conditional<ALGO == ALGO_MVDR, float, double>::type T;
@@ -285,7 +308,7 @@ __global__ void __launch_bounds__(SsCfg<ALGO>::kThreads, 1) sel_stream_kernel(co
     };
     if (have && use_tma && npairs > 0 && lane == 0) issue(p.hop_begin);
 
-    if (is_mic) {
+    if (is_mic && ALGO != ALGO_GSS) {
       // ---- history of the previous calls: global ring (slot = frame % D) -> tensor memory (slot = frame % Dt) ----
 #pragma unroll 1
       for (int j = 1; j <= p.P; j++) {
@@ -414,7 +437,8 @@ __global__ void __launch_bounds__(SsCfg<ALGO>::kThreads, 1) sel_stream_kernel(co
       // ================================================================== microphone warps only from here
       int sx = sig0 + 2 * ip;
       sx %= Dt;                                     // ring slot of frame t
-      const int sx1 = (sx + 1 == Dt) ? 0 : sx + 1;  // ring slot of frame t+1 (it still holds frame t-P)
+      int sx1 = (sx + 1 == Dt) ? 0 : sx + 1;        // ring slot of frame t+1 (it still holds frame t-P)
+      if (ALGO == ALGO_GSS) { sx = 0; sx1 = 1; }    // gss keeps no history: slots 0 / 1 just park X_t / X_{t+1} until the staging
       // v[k2] = Z[32*k2 + lane], Z = FFT(0.5*w*(x_t + i x_{t+1})).  X_t[l] = Z[l] + conj(Z[N-l]), X_{t+1}[l] = -i (Z[l] - conj(Z[N-l]));
       // Z[N-l] sits in lane (32 - lane) % 32, register 31 - k2 (lane 0: its own register (32 - k2) % 32).
       if (m == 0) {
@@ -548,9 +572,14 @@ __global__ void __launch_bounds__(SsCfg<ALGO>::kThreads, 1) sel_stream_kernel(co
             }
             if (mine && idx / kSsItems == q) {
               float2* dst = &bt.item[idx % kSsItems][m];
+              if (ALGO == ALGO_GSS) {
+                dst[0] = make_float2(__uint_as_float(r[0]), __uint_as_float(r[1]));   // X_t (slot 0)
+                dst[8] = xn;                                                              // X_{t+1}
+              } else {
 #pragma unroll
-              for (int e = 0; e < kSsSlots; e++) dst[e * 8] = make_float2(__uint_as_float(r[2 * e]), __uint_as_float(r[2 * e + 1]));
-              dst[kSsSlots * 8] = xn;
+                for (int e = 0; e < kSsSlots; e++) dst[e * 8] = make_float2(__uint_as_float(r[2 * e]), __uint_as_float(r[2 * e + 1]));
+                dst[kSsSlots * 8] = xn;
+              }
               if (m == 0) {
                 bt.bin[idx % kSsItems] = (unsigned short)(k2 * 32 + lane);
                 bt.flags[idx % kSsItems] = (unsigned char)(((sh.masks[0][k2] >> lane) & 1u) | (((sh.masks[1][k2] >> lane) & 1u) << 1));
@@ -558,7 +587,7 @@ __global__ void __launch_bounds__(SsCfg<ALGO>::kThreads, 1) sel_stream_kernel(co
             }
           }
         }
-        if (two) tmem_st2(tm + (uint32_t)((k2 * kSsSlots + sx1) * 2), xn.x, xn.y);   // history append of frame t+1
+        if (two && ALGO != ALGO_GSS) tmem_st2(tm + (uint32_t)((k2 * kSsSlots + sx1) * 2), xn.x, xn.y);   // history append of frame t+1
       }
       if (cur_q >= 0) ss_publish((seq0 + cur_q) % kSsSolvers);
       seq0 += nbat;
@@ -574,7 +603,7 @@ __global__ void __launch_bounds__(SsCfg<ALGO>::kThreads, 1) sel_stream_kernel(co
       }
     }
     // ---- state for the next call: the last min(nh, P) frames go back to the global ring; the overlap-add tail ----
-    if (have) {
+    if (have && ALGO != ALGO_GSS) {
       const int nsave = min(nh, p.P);
       const int a0 = (sig0 + nh - 1) % Dt;           // ring slot (tensor memory) of the launch's last frame
       const int g0 = (p.ring_slot0 + nh - 1) % D;    // its slot in the global ring
@@ -610,7 +639,8 @@ __global__ void __launch_bounds__(SsCfg<ALGO>::kThreads, 1) sel_stream_kernel(co
       if (tot >= 0 && n >= tot) break;
       const SsBatch& bt = sh.batch[w];
       const int ky = bt.ybuf;
-      ss_solve_batch<ALGO>(p, sh, bt, lane);
+      if constexpr (ALGO == ALGO_GSS) ss_solve_batch_gss(p, sh, bt, lane, s);
+      else ss_solve_batch<ALGO>(p, sh, bt, lane);
       __syncwarp();
       if (lane == 0) {
         __threadfence_block();
@@ -631,7 +661,9 @@ size_t sel_stream_smem() { return sizeof(SsShared) + 128; }
 // 100-16 000 Hz -> bins 3..341) and the pseudo-bin must be outside it.
 bool sel_stream_supported(const KernelParams& p, int algo, const uint8_t* inband_host) {
   if (getenv("BF_SEL_OLD")) return false;
-  if (!(p.H == 512 && p.M <= 8 && p.P >= 1 && p.P + 1 <= kSsSlots && algo == ALGO_MVDR)) return false;
+  // gss was tried on this pipeline (W recursion by one solver lane per bin): 189 k audio-s/s against 248 k in sel_pairs_kernel, whose
+  // 512 threads per SM keep far more of the latency-bound W loads in flight; it stays there
+  if (!(p.H == 512 && p.M <= 8 && algo == ALGO_MVDR && p.P >= 1 && p.P + 1 <= kSsSlots)) return false;
   for (int l = kSsBins; l < kL1K; l++)
     if (inband_host[l]) return false;
   return true;
