@@ -20,8 +20,15 @@ for r in rows[1:]:
     if not any(k in r[iK] for k in ("bf::", "das_pairs_kernel", "sel_pairs_kernel", "sel_stream_kernel", "frames_kernel", "srp_", "save_prev_hop", "gss_reset", "zero_hops", "ref_kernel", "gsc_")):
         continue
     per[(r[iID], r[iK])][r[iM]] = float(r[iV].replace(",", "")) * scale.get(r[iU], 1.0)
+# bench.py also launches a small selection-density probe (16 streams): only launches of at least half the kernel's longest
+# duration count as "the bench shape"
+tmax = defaultdict(float)
+for (_, k), m in per.items():
+    tmax[k] = max(tmax[k], m.get("gpu__time_duration.sum", 0.0))
 agg = defaultdict(lambda: [0, 0.0, 0.0, 0.0])
 for (_, k), m in per.items():
+    if m.get("gpu__time_duration.sum", 0.0) < 0.5 * tmax[k]:
+        continue
     a = agg[k]
     a[0] += 1
     a[1] += m.get("gpu__time_duration.sum", 0.0)
