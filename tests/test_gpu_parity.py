@@ -604,3 +604,23 @@ def test_cpp_drop_in_nodes_match_reference_golden(name, seam):
     assert err <= REL_L2_TOL
     if algo in ("lcmv", "gss"):
         assert interf == list(_GOLD[name + "/interf"]), "interference list must be bit-exact"
+
+
+def test_srp_closed_loop_follows_a_moving_source():
+    """the steered-response arg-max drives bf_set_theta (what scripts/energy2theta*.py do by gradient search)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("srp_steer", _os.path.join(_os.path.dirname(_os.path.dirname(_os.path.abspath(__file__))), "tools", "srp_steer.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    xy = bf.GEOMETRIES["circ8"]
+    a = synth_stream(xy, 64 * H, sources=((30.0, 0.1, 190.0, 30),), lead_in=0, seed=1)
+    b = synth_stream(xy, 64 * H, sources=((-70.0, 0.1, 190.0, 30),), lead_in=0, seed=2)
+    cfg = bf.make_config("das", mics="circ8")
+    y, track = mod.follow(cfg, np.concatenate([a, b], axis=1), block_hops=8)
+    assert y.shape == (128 * H,) and np.isfinite(y).all()
+    assert abs(track[6] - 30.0) <= 6.0, track          # settled on the first source
+    assert abs(track[-1] + 70.0) <= 6.0, track         # ... and followed it to the second position
+    # the loop's output equals the oracle run with the same theta schedule (set_theta before block k applies from its first hop)
+    events = [(8 * k, "theta", float(th)) for k, th in enumerate(track)]
+    ref = Oracle(cfg).process(np.concatenate([a, b], axis=1), events=events)
+    assert rel_l2(y, ref) <= REL_L2_TOL
