@@ -244,7 +244,8 @@ __global__ void __launch_bounds__(SsCfg<ALGO>::kThreads, 1) sel_stream_kernel(co
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int M = p.M, D = p.ring_depth, Dt = p.P + 1;
   constexpr int H = 512;
-  const int s = blockIdx.x + p.stream_begin;
+  // persistent CTAs: CTA c owns streams c, c + gridDim.x, ...; the pipeline keeps running across stream boundaries (no drain)
+  const int s_first = blockIdx.x + p.stream_begin, s_end = p.stream_begin + p.n_streams;
   const int nh = p.hop_end - p.hop_begin;
   const int npairs = (nh + 1) >> 1;
   const int sig0 = p.frame_index0 % Dt;   // tensor-memory ring slot of the launch's first frame
@@ -261,7 +262,6 @@ __global__ void __launch_bounds__(SsCfg<ALGO>::kThreads, 1) sel_stream_kernel(co
     sh.inband[i] = inb ? 1 : 0;
     sh.ygain[i] = inb ? 0.01f : ((ALGO == ALGO_MVDR && i == 0) ? 1.0f : 0.0f);
   }
-  for (int i = tid; i < H; i += kSsThreads) sh.tail[i] = p.tail[(size_t)s * H + i];
   for (int i = tid; i < kSsKY * 2 * kL1K; i += kSsThreads) (&sh.y[0][0][0])[i] = make_float2(0.f, 0.f);   // bins outside the band stay 0 (mvdr.cpp:103)
   if (tid < kSsKY) { sh.nonfinite[tid][0] = 0; sh.nonfinite[tid][1] = 0; }
   if (tid == 0) {
@@ -291,23 +291,30 @@ __global__ void __launch_bounds__(SsCfg<ALGO>::kThreads, 1) sel_stream_kernel(co
     float2* tile = sh.tile[is_mic ? warp : kSsMicWarps];
     float* stage = reinterpret_cast<float*>(tile);
     float2* xpark = reinterpret_cast<float2*>(&sh.mags[m][0][0]);   // X_{t+1} of this microphone between the gate and the staging
-    const float* in_s = p.in + (size_t)s * p.in_stream_stride + (size_t)m * p.in_mic_stride;
-    float2* hist_s = p.hist + (size_t)s * D * M * p.Lsel + (size_t)m * p.Lsel;   // + slot*M*Lsel + sel_slot[l]
     double sd, cd;
     sincospi((double)lane / 1024.0, &sd, &cd);
     // analysis window * 0.5 (microphones) / synthesis window * out_amp / N (inverse)
     const float s_w = is_mic ? (float)(0.5 * sd) : (float)(sd * p.out_scale), c_w = is_mic ? (float)(0.5 * cd) : (float)(cd * p.out_scale);
 
-    auto issue = [&](int t) {   // hops t-1..t+1 of this microphone -> tile (hop -1 = per-stream state, util.h:275-277)
+    auto issue = [&](int sx, int t) {   // hops t-1..t+1 of this microphone of stream sx -> tile (hop -1 = per-stream state, util.h:275-277)
+      const float* base = p.in + (size_t)sx * p.in_stream_stride + (size_t)m * p.in_mic_stride;
       const bool two = t + 1 < p.hop_end;
       const uint32_t nb = (two ? 2u : 1u) * H * 4u;
       mbar_expect_tx(&sh.tma_bar[m], nb + H * 4u);
-      const float* prev = (t - 1 < 0) ? p.prev_hop + ((size_t)s * M + m) * H : in_s + (size_t)(t - 1) * H;
+      const float* prev = (t - 1 < 0) ? p.prev_hop + ((size_t)sx * M + m) * H : base + (size_t)(t - 1) * H;
       bulk_g2s(stage, prev, H * 4u, &sh.tma_bar[m]);
-      bulk_g2s(stage + H, in_s + (size_t)t * H, nb, &sh.tma_bar[m]);
+      bulk_g2s(stage + H, base + (size_t)t * H, nb, &sh.tma_bar[m]);
     };
-    if (have && use_tma && npairs > 0 && lane == 0) issue(p.hop_begin);
+    if (have && use_tma && npairs > 0 && lane == 0 && s_first < s_end) issue(s_first, p.hop_begin);
 
+    int seq0 = 0;   // staging batches published so far (identical in every microphone warp)
+    int gp0 = 0;    // frame pairs this CTA has been through before the current stream
+#pragma unroll 1
+    for (int s = s_first; s < s_end; s += gridDim.x, gp0 += npairs) {
+    const float* in_s = p.in + (size_t)s * p.in_stream_stride + (size_t)m * p.in_mic_stride;
+    float2* hist_s = p.hist + (size_t)s * D * M * p.Lsel + (size_t)m * p.Lsel;   // + slot*M*Lsel + sel_slot[l]
+    if (is_inv)
+      for (int i = lane; i < H; i += 32) sh.tail[i] = p.tail[(size_t)s * H + i];
     if (is_mic && ALGO != ALGO_GSS) {
       // ---- history of the previous calls: global ring (slot = frame % D) -> tensor memory (slot = frame % Dt) ----
 #pragma unroll 1
@@ -329,12 +336,12 @@ __global__ void __launch_bounds__(SsCfg<ALGO>::kThreads, 1) sel_stream_kernel(co
       tmem_wait_st();
     }
 
-    int seq0 = 0;   // staging batches published so far (identical in every microphone warp)
 #pragma unroll 1
     for (int ip = 0; ip < npairs; ip++) {
+      const int gp = gp0 + ip;   // pair counter of the CTA: buffer rotation and barrier parities run across streams
       const int t = p.hop_begin + 2 * ip;
       const bool two = t + 1 < p.hop_end;
-      const int ky = ip % kSsKY;
+      const int ky = gp % kSsKY;
       float2 v[32];
       float e0 = 0.f, e1 = 0.f;
       bool z0 = false, z1 = false;
@@ -342,7 +349,7 @@ __global__ void __launch_bounds__(SsCfg<ALGO>::kThreads, 1) sel_stream_kernel(co
         // ---------------------------------------------------------------- hops -> windowed packed frame pair
         if (have) {
           if (use_tma) {
-            ss_wait(&sh.tma_bar[m], ip & 1);
+            ss_wait(&sh.tma_bar[m], gp & 1);
           } else {   // unaligned caller buffers: plain warp copy, no prefetch
             const float* prev = (t - 1 < 0) ? p.prev_hop + ((size_t)s * M + m) * H : in_s + (size_t)(t - 1) * H;
             for (int i = lane; i < H; i += 32) {
@@ -373,7 +380,7 @@ __global__ void __launch_bounds__(SsCfg<ALGO>::kThreads, 1) sel_stream_kernel(co
         if (lane == 0) { sh.sqrtE[0][m] = 2.0f * sqrtf(e0); sh.sqrtE[1][m] = 2.0f * sqrtf(e1); }
       } else {
         // ---------------------------------------------------------------- output spectra of the pair -> G = Yh_t + i Yh_{t+1}
-        ss_wait(&sh.y_done[ky], (uint32_t)(ip / kSsKY) & 1u);   // defaults written and every batch of the pair solved
+        ss_wait(&sh.y_done[ky], (uint32_t)(gp / kSsKY) & 1u);   // defaults written and every batch of the pair solved
         // one inf/NaN bin makes the reference's whole inverse frame NaN; the two frames of a pair share one complex transform
         // here, so a poisoned frame is left out of G and re-poisoned at the output without touching its partner
         z0 = *reinterpret_cast<volatile int*>(&sh.nonfinite[ky][0]) != 0;
@@ -412,9 +419,9 @@ __global__ void __launch_bounds__(SsCfg<ALGO>::kThreads, 1) sel_stream_kernel(co
       ss_fft1024_fwd(v, tile, sh.tw, lane, [&]() {
         // the exchange tile is free until the next pair: its hops start to arrive now, behind the second FFT pass,
         // the gate and the staging of this pair
-        if (have && use_tma && ip + 1 < npairs && lane == 0) {
+        if (have && use_tma && lane == 0 && (ip + 1 < npairs || s + (int)gridDim.x < s_end)) {
           fence_proxy_async();
-          issue(t + 2);
+          if (ip + 1 < npairs) issue(s, t + 2); else issue(s + (int)gridDim.x, p.hop_begin);   // ... or the first pair of the CTA's next stream
         }
       });
       if (is_inv) {
@@ -442,7 +449,7 @@ __global__ void __launch_bounds__(SsCfg<ALGO>::kThreads, 1) sel_stream_kernel(co
       // v[k2] = Z[32*k2 + lane], Z = FFT(0.5*w*(x_t + i x_{t+1})).  X_t[l] = Z[l] + conj(Z[N-l]), X_{t+1}[l] = -i (Z[l] - conj(Z[N-l]));
       // Z[N-l] sits in lane (32 - lane) % 32, register 31 - k2 (lane 0: its own register (32 - k2) % 32).
       if (m == 0) {
-        if (ip >= kSsKY) ss_wait(&sh.y_free[ky], (uint32_t)((ip / kSsKY) - 1) & 1u);
+        if (gp >= kSsKY) ss_wait(&sh.y_free[ky], (uint32_t)((gp / kSsKY) - 1) & 1u);
         // a non-finite input sample of microphone 0 makes every default output of the frame non-finite (SURVEY B-10)
         if (!isfinite(e0)) sh.nonfinite[ky][0] = 1;
         if (two && !isfinite(e1)) sh.nonfinite[ky][1] = 1;
@@ -512,8 +519,6 @@ __global__ void __launch_bounds__(SsCfg<ALGO>::kThreads, 1) sel_stream_kernel(co
         }
       }
       named_bar_sync(2, kSsMicWarps * 32);   // selection masks complete; nobody reads the magnitudes any more
-#pragma unroll
-      for (int k2 = 0; k2 < kSsBlocks; k2++) xpark[k2 * 32 + lane] = x1[k2];
       if (p.capture) {   // diagnostics: one byte per FFT bin and frame, bit 0 = selected
         for (int k2 = m; k2 <= 16; k2 += kSsMicWarps) {
           const int l = k2 * 32 + lane;
@@ -543,11 +548,23 @@ __global__ void __launch_bounds__(SsCfg<ALGO>::kThreads, 1) sel_stream_kernel(co
       // defaults written, batch count known: this arrival stands for every batch the pair does NOT have (the solvers arrive once per batch)
       if (m == 0 && lane == 0) mbar_arrive_cnt(&sh.y_done[ky], (uint32_t)(kSsYDoneCount - nbat));
       int cur_q = -1;
+      // Blocks without a selected bin (most of them) only append X_{t+1} to the history, straight from the registers; the
+      // blocks with selected bins park X_{t+1} in this microphone's (now idle) magnitude rows and go through the rolled
+      // staging loop below, which reads the history BEFORE the append overwrites the slot of frame t-P.
+      unsigned bmask = __ballot_sync(0xffffffffu, emask != 0u);   // bit k2: block k2 has a bin selected in either frame
+      static_for<0, kSsBlocks>([&](auto k2c) {
+        constexpr int k2 = decltype(k2c)::value;
+        if ((bmask >> k2) & 1u) xpark[k2 * 32 + lane] = x1[k2];
+        else if (two && ALGO != ALGO_GSS) tmem_st2(tm + (uint32_t)((k2 * kSsSlots + sx1) * 2), x1[k2].x, x1[k2].y);
+      });
+      __syncwarp();
 #pragma unroll 1
-      for (int k2 = 0; k2 < kSsBlocks; k2++) {
+      while (bmask) {
+        const int k2 = __ffs(bmask) - 1;
+        bmask &= bmask - 1;
         const unsigned em = __shfl_sync(0xffffffffu, emask, k2);
         const float2 xn = xpark[k2 * 32 + lane];
-        if (em) {   // warp-uniform
+        {
           const int bbase = __shfl_sync(0xffffffffu, base_excl, k2);
           uint32_t r[24];
           tmem_ld16(tm + (uint32_t)(k2 * kSsSlots * 2), r);
@@ -593,15 +610,6 @@ __global__ void __launch_bounds__(SsCfg<ALGO>::kThreads, 1) sel_stream_kernel(co
       seq0 += nbat;
       tmem_wait_st();
     }
-    if (is_mic) {
-      // end of the stream: one more arrival per slot releases its solver, which leaves when its next batch number reaches the total
-      if (m == 0 && lane == 0) *reinterpret_cast<volatile int*>(&sh.total_batches) = seq0;
-      for (int w = 0; w < kSsSolvers; w++) {
-        const int rounds = seq0 > w ? (seq0 - w + kSsSolvers - 1) / kSsSolvers : 0;   // batches that went through slot w
-        if (rounds >= 1) ss_wait(&sh.empty[w], (uint32_t)(rounds - 1) & 1u);
-        ss_publish(w);
-      }
-    }
     // ---- state for the next call: the last min(nh, P) frames go back to the global ring; the overlap-add tail ----
     if (have && ALGO != ALGO_GSS) {
       const int nsave = min(nh, p.P);
@@ -626,8 +634,21 @@ __global__ void __launch_bounds__(SsCfg<ALGO>::kThreads, 1) sel_stream_kernel(co
         }
       }
     }
-    if (is_inv)
+    if (is_inv) {
+      __syncwarp();
       for (int i = lane; i < H; i += 32) p.tail[(size_t)s * H + i] = sh.tail[i];
+      __syncwarp();
+    }
+    }   // streams of this CTA
+    if (is_mic) {
+      // end of the CTA's last stream: one more arrival per slot releases its solver, which leaves when its next batch number reaches the total
+      if (m == 0 && lane == 0) *reinterpret_cast<volatile int*>(&sh.total_batches) = seq0;
+      for (int w = 0; w < kSsSolvers; w++) {
+        const int rounds = seq0 > w ? (seq0 - w + kSsSolvers - 1) / kSsSolvers : 0;   // batches that went through slot w
+        if (rounds >= 1) ss_wait(&sh.empty[w], (uint32_t)(rounds - 1) & 1u);
+        ss_publish(w);
+      }
+    }
   } else {
     // ================================================================== solver warps
     const int w = warp - kSsMicWarps;
@@ -639,7 +660,7 @@ __global__ void __launch_bounds__(SsCfg<ALGO>::kThreads, 1) sel_stream_kernel(co
       if (tot >= 0 && n >= tot) break;
       const SsBatch& bt = sh.batch[w];
       const int ky = bt.ybuf;
-      if constexpr (ALGO == ALGO_GSS) ss_solve_batch_gss(p, sh, bt, lane, s);
+      if constexpr (ALGO == ALGO_GSS) ss_solve_batch_gss(p, sh, bt, lane, p.stream_begin + (int)blockIdx.x);
       else ss_solve_batch<ALGO>(p, sh, bt, lane);
       __syncwarp();
       if (lane == 0) {
@@ -679,7 +700,10 @@ cudaError_t launch_sel_stream(int algo, const KernelParams& p, cudaStream_t st) 
   }
   cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  k<<<p.n_streams, SsCfg<ALGO_MVDR>::kThreads, smem, st>>>(p, use_tma);
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  k<<<p.n_streams < sms ? p.n_streams : sms, SsCfg<ALGO_MVDR>::kThreads, smem, st>>>(p, use_tma);   // one persistent CTA per SM
   return cudaGetLastError();
 }
 
