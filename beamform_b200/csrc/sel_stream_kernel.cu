@@ -478,7 +478,6 @@ __global__ void __launch_bounds__(SsCfg<ALGO>::kThreads, 1) sel_stream_kernel(co
           }
         });
       }
-      tmem_wait_st();
       named_bar_sync(1, kSsMicWarps * 32);   // magnitudes of all microphones complete
       // ---------------------------------------------------------------- gate (mvdr.cpp:79-85), FP64 re-decision inside the guard band
       {
@@ -558,6 +557,7 @@ __global__ void __launch_bounds__(SsCfg<ALGO>::kThreads, 1) sel_stream_kernel(co
         else if (two && ALGO != ALGO_GSS) tmem_st2(tm + (uint32_t)((k2 * kSsSlots + sx1) * 2), x1[k2].x, x1[k2].y);
       });
       __syncwarp();
+      tmem_wait_st();   // the appends of frame t (issued before the gate) must have landed before the staging reads them back
 #pragma unroll 1
       while (bmask) {
         const int k2 = __ffs(bmask) - 1;

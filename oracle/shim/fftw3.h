@@ -17,7 +17,7 @@ typedef double fftw_complex[2];
 struct bfshim_fftw_plan_s {
   int n, sign;
   std::complex<double>*in, *out;
-  std::vector<std::complex<double> > tw, scratch;
+  std::vector<std::complex<double> > tw, scratch, work;
 };
 typedef bfshim_fftw_plan_s* fftw_plan;
 static inline void* fftw_malloc(size_t n) { return calloc(n + 64, 1); }   // +64: phasempf.cpp:274 writes y_fft[fft_win]
@@ -50,9 +50,10 @@ static inline void fftw_execute(const fftw_plan p) {
     for (int k = 0; k < n; k++) p->out[k] = p->scratch[k];
     return;
   }
-  // Stockham: ping-pong between out and scratch; stage with l butterflies groups of stride m
-  std::vector<cd> a(p->in, p->in + n);
-  cd* x = a.data();
+  // Stockham: ping-pong between two plan-owned buffers (no allocation per call); stage with l butterfly groups of stride m
+  if ((int)p->work.size() != n) p->work.resize(n);
+  for (int k = 0; k < n; k++) p->work[k] = p->in[k];
+  cd* x = p->work.data();
   cd* y = p->scratch.data();
   for (int l = n / 2, m = 1; l >= 1; l >>= 1, m <<= 1) {
     for (int j = 0; j < l; j++) {

@@ -440,7 +440,8 @@ def test_full_size_c1_das():
 
 
 def test_full_size_c2_mvdr_batched_1k_streams():
-    _full_size_case("mvdr", "circ8", 1184, 188, 512, spot=(0, 1183))
+    # 1184 streams on 148 persistent CTAs: eight streams per CTA; the spot streams cover first / middle / last positions of a CTA's sequence
+    _full_size_case("mvdr", "circ8", 1184, 188, 512, spot=(0, 1, 147, 148, 149, 295, 296, 500, 591, 592, 740, 887, 888, 1035, 1036, 1183))
 
 
 def test_full_size_c3_lcmv_and_gss():
