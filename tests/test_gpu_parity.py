@@ -625,3 +625,20 @@ def test_srp_closed_loop_follows_a_moving_source():
     events = [(8 * k, "theta", float(th)) for k, th in enumerate(track)]
     ref = Oracle(cfg).process(np.concatenate([a, b], axis=1), events=events)
     assert rel_l2(y, ref) <= REL_L2_TOL
+
+
+@pytest.mark.parametrize("kw", [dict(past_windows=4), dict(past_windows=1), dict(past_windows=7, freq_min=400, freq_max=4000),
+                                dict(freq_max=20000), dict(past_windows=12), dict(freq_min=1000, freq_max=16400)])
+def test_mvdr_parameter_corners_match_oracle(kw):
+    """The pipelined kernel keeps P + 1 <= 11 ring slots per bin in tensor memory for bins below 352: shorter histories (ring arithmetic
+    modulo P + 1), narrower bands, a band edge in the last on-chip block, and the shapes outside it (P > 10, band above bin 351), which
+    run sel_pairs_kernel -- all against the oracle, split into three calls so that the ring is saved and reloaded."""
+    cfg = bf.make_config("mvdr", mics="circ8", initial_angle=15.0, **kw)
+    x = synth_batch(bf.GEOMETRIES["circ8"], 3, 47 * H, seed=77)
+    ref, sel, _ = oracle_with_flags(cfg, x)
+    b = bf.Beamformer(cfg, n_streams=3)
+    got = np.concatenate([b.process(x[:, :, :13 * H]), b.process(x[:, :, 13 * H:14 * H]), b.process(x[:, :, 14 * H:])], axis=1)
+    assert sel.sum() > 300
+    err = finite_rel_l2(got, ref)
+    print("mvdr", kw, "rel_l2", err, "selected", int(sel.sum()))
+    assert err <= REL_L2_TOL
