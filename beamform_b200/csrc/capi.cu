@@ -39,6 +39,8 @@ int frames_kernel_sel_chunk(int N, int M);
 cudaError_t launch_frames_kernel_sel(int algo, const KernelParams& p, cudaStream_t st);
 size_t frames_kernel_sel_smem(int N, int M);
 cudaError_t launch_frames_kernel_mcra(const KernelParams& p, cudaStream_t st);
+bool phase_n_supported(const KernelParams& p, int algo);
+cudaError_t launch_phase_n(int algo, const KernelParams& p, cudaStream_t st);
 cudaError_t launch_ref_kernel(const KernelParams& p, cudaStream_t st);
 cudaError_t launch_gsc(const KernelParams& p, cudaStream_t st);
 size_t gsc_align_smem(int N, int M);
@@ -791,6 +793,7 @@ static int run_segment(bf_handle* h, const float* in, size_t ss, size_t ms, floa
   bool swap_tails = false;
   static const bool force_generic = getenv("BF_GENERIC") != nullptr;   // debug: cross-check the generic kernel at N = 1024
   const bool gen_algo = h->cfg.algo == BF_ALGO_DAS || h->cfg.algo == BF_ALGO_PHASE || h->cfg.algo == BF_ALGO_PHASEMPF;
+  const bool phase_f64 = getenv("BF_PHASE_F64") != nullptr;   // tests: the double-spectra / 1024-point CTA kernels instead of phase_n_kernel (read per launch)
   static const bool force_sel_generic = getenv("BF_SEL_GENERIC") != nullptr;   // debug: cross-check the general gated kernel
   const bool sel_algo = h->cfg.algo == BF_ALGO_MVDR || h->cfg.algo == BF_ALGO_LCMV || h->cfg.algo == BF_ALGO_GSS;
   if (h->cfg.algo == BF_ALGO_GSC) {
@@ -820,6 +823,7 @@ static int run_segment(bf_handle* h, const float* in, size_t ss, size_t ms, floa
     }
     CUDA_TRY(bf::launch_frames_kernel_sel(h->cfg.algo, p, st));
   }
+  else if (!phase_f64 && bf::phase_n_supported(p, h->cfg.algo)) CUDA_TRY(bf::launch_phase_n(h->cfg.algo, p, st));   // FP32 spectra, 3 CTAs per SM
   else if (h->N != 1024 || (force_generic && gen_algo)) CUDA_TRY(bf::launch_frames_kernel_n(h->cfg.algo, p, st));
   else if (h->cfg.algo == BF_ALGO_DAS && bf::das_pairs_supported(p)) {
     // a stream's first and last pair may belong to different warps: the new tails go to the second buffer (no

@@ -292,6 +292,27 @@ def test_other_frame_sizes_match_oracle(algo, mics, hop, kw):
     assert err <= REL_L2_TOL
 
 
+@pytest.mark.parametrize("env", ["BF_PHASE_F32", "BF_PHASE_F64"])
+@pytest.mark.parametrize("algo,mics,hop,kw", [("phase", "aira3", 512, dict(mag_threshold=0.002)), ("phase", "binaural", 2048, dict(mag_threshold=0.002)),
+                                              ("phasempf", "binaural", 2048, {}), ("phasempf", "aira3", 512, {}), ("phasempf", "aira3", 1024, {})])
+def test_phase_kernels_both_precisions(monkeypatch, env, algo, mics, hop, kw):
+    """The phase-mask nodes have two kernels per frame size: FP32 spectra with exact re-decisions (phase_n_kernel, default up
+    to 1024 points, BF_PHASE_F32 forces it for longer frames) and the double-spectra / CTA-per-stream kernels (default for
+    longer frames, BF_PHASE_F64 forces them).  Both must match the oracle, masks included."""
+    monkeypatch.setenv(env, "1")
+    cfg = bf.make_config(algo, mics=mics, hop=hop, initial_angle=15.0, **kw)
+    n_hops = 61 if algo != "phasempf" else 130
+    x = np.stack([synth_stream(bf.GEOMETRIES[mics], n_hops * hop, seed=700 + b, gate_hz=1.3 if algo == "phasempf" else 0.0) for b in range(2)])
+    ref, _, msk = oracle_with_flags(cfg, x)
+    got, flags, _ = run_device(cfg, x, H=hop)
+    kept = (flags >> 1) & 1
+    mism = int((kept != msk).sum())
+    err = rel_l2(got, ref)
+    print(env, algo, mics, "hop", hop, "rel_l2", err, "mask mismatches", mism, "of", msk.size)
+    assert err <= REL_L2_TOL
+    assert mism <= MASK_MISMATCH_FRAC * msk.size
+
+
 @pytest.mark.parametrize("algo,mics,hop,interf,events", [
     ("mvdr", "circ8", 1024, (), ()), ("mvdr", "aira3", 256, (), ()), ("mvdr", "circ12", 512, (), ()), ("mvdr", "circ16", 512, (), ()),
     ("lcmv", "circ8", 256, (80.0, -60.0, 150.0), ((15, "theta", 20.0), (25, "interf", 2, -55.0), (35, "interf", 4, 120.0), (45, "interf", 1, 119.5))),
