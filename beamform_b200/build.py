@@ -10,7 +10,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libbeamform_b200.so")
-SOURCES = ["capi.cu", "frames_kernel.cu", "das_kernel.cu", "sel_kernel.cu", "sel_stream_kernel.cu", "generic_kernel.cu", "phase_n_kernel.cu", "srp_kernel.cu", "srp_tc_kernel.cu"]
+SOURCES = ["capi.cu", "frames_kernel.cu", "das_kernel.cu", "sel_kernel.cu", "sel_stream_kernel.cu", "generic_kernel.cu", "phase_n_kernel.cu", "mcra_kernel.cu", "srp_kernel.cu", "srp_tc_kernel.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC", "-shared",

@@ -39,6 +39,8 @@ int frames_kernel_sel_chunk(int N, int M);
 cudaError_t launch_frames_kernel_sel(int algo, const KernelParams& p, cudaStream_t st);
 size_t frames_kernel_sel_smem(int N, int M);
 cudaError_t launch_frames_kernel_mcra(const KernelParams& p, cudaStream_t st);
+bool mcra_pairs_supported(const KernelParams& p);
+cudaError_t launch_mcra_pairs(const KernelParams& p, cudaStream_t st, int sm_count);
 bool phase_n_supported(const KernelParams& p, int algo);
 cudaError_t launch_phase_n(int algo, const KernelParams& p, cudaStream_t st);
 cudaError_t launch_ref_kernel(const KernelParams& p, cudaStream_t st);
@@ -812,7 +814,10 @@ static int run_segment(bf_handle* h, const float* in, size_t ss, size_t ms, floa
     p.gsc_vad_threshold = h->cfg.vad_threshold; p.gsc_mu0 = h->cfg.mu0; p.gsc_mu_max = h->cfg.mu_max;
     CUDA_TRY(bf::launch_gsc(p, st));
     h->launches++;
-  } else if (h->cfg.algo == BF_ALGO_MCRA) CUDA_TRY(bf::launch_frames_kernel_mcra(p, st));
+  } else if (h->cfg.algo == BF_ALGO_MCRA) {
+    if (bf::mcra_pairs_supported(p)) CUDA_TRY(bf::launch_mcra_pairs(p, st, h->sm_count));   // 1024-point frames: a warp per stream
+    else CUDA_TRY(bf::launch_frames_kernel_mcra(p, st));
+  }
   else if (h->cfg.algo == BF_ALGO_REF) CUDA_TRY(bf::launch_ref_kernel(p, st));
   else if (sel_algo && (h->N != 1024 || force_sel_generic || (h->M > 8 && h->cfg.algo != BF_ALGO_GSS) || h->C > 8)) {   // > 7 interferers: general kernel
     p.sel_chunk = bf::frames_kernel_sel_chunk((int)h->N, (int)h->M);

@@ -55,14 +55,14 @@ WORKLOADS = {
                n_streams=100, hops=188, passes=1, kernel="srp_power_tc_kernel", srp_dirs=360),
     # SURVEY.md section 8f rank 2 (single-channel nodes: 2 x 4 algorithmic bytes per sample)
     "mcra": dict(name="MCRA node (mcra.launch), first microphone of aira3, 1024-pt", algo="mcra", mics="aira3", n_streams=2368, hops=188, passes=8,
-                 kernel="frames_kernel_mcra<1024>", alg_channels=1),
+                 kernel="mcra_pairs_kernel", alg_channels=1),
     "ref": dict(name="rosjack_ref passthrough (window^2 overlap-add), first microphone of aira3", algo="ref", mics="aira3", n_streams=2368,
                 hops=188, passes=64, kernel="ref_kernel", alg_channels=1),
     # SURVEY.md section 8f rank 1
     "gsc": dict(name="GSC 3-mic (aira3) 1024-pt: per-microphone alignment + 128-tap NLMS (gsc.launch)", algo="gsc", mics="aira3", n_streams=4736,
                 hops=94, passes=1, kernel="gsc_nlms_kernel (+ gsc_align_kernel<1024>)"),
     "ph": dict(name="Phase 3-mic (aira3) 1024-pt phase mask", algo="phase", mics="aira3", n_streams=1184, hops=188, passes=8,
-               kernel="frames_kernel_1024<phase>"),
+               kernel="phase_n_kernel<phase,1024,3>"),
 }
 EXTRA = ("c1", "c3l", "c3g", "c4", "c5")   # the other BASELINE.json configs, reported under "workloads" by the default run
 

@@ -352,6 +352,25 @@ def test_mcra_and_ref_nodes_match_oracle(algo, mics, hop, kw):
     assert err <= (0.0 if algo == "ref" else REL_L2_TOL)   # rosjack_ref is elementwise float arithmetic: bit-exact
 
 
+@pytest.mark.parametrize("kw", [dict(L=50), dict(L=7, out_only_noise=True), {}])
+def test_mcra_1024_both_kernels(monkeypatch, kw):
+    """1024-point MCRA runs the warp-per-stream kernel (mcra_pairs_kernel); BF_MCRA_OLD keeps the CTA-per-stream kernel.  Both
+    must match the oracle, with more streams than one CTA has warps, odd hop counts and state carried across calls."""
+    cfg = bf.make_config("mcra", mics="aira3", hop=512, **kw)
+    n_hops = 131
+    x = np.stack([synth_stream(bf.GEOMETRIES["aira3"], n_hops * 512, seed=640 + b, gate_hz=1.3) for b in range(11)])
+    ref = oracle_batch(cfg, x)
+    for old in (False, True):
+        if old:
+            monkeypatch.setenv("BF_MCRA_OLD", "1")
+        b = bf.Beamformer(cfg, n_streams=11)
+        k = 21 * 512
+        got = np.concatenate([b.process(x[:, :, :k]), b.process(x[:, :, k:k + 512]), b.process(x[:, :, k + 512:])], axis=1)
+        err = rel_l2(got, ref)
+        print("mcra 1024", kw, "old kernel" if old else "warp kernel", "rel_l2", err)
+        assert err <= REL_L2_TOL
+
+
 @pytest.mark.parametrize("mics,hop,kw,events", [("aira3", 512, {}, ((20, "theta", 25.0),)), ("circ8", 256, dict(initial_angle=-35.0, filter_size=64), ()),
                                                 ("binaural", 2048, dict(use_vad=True, vad_threshold=0.08), ()), ("circ12", 512, dict(filter_size=256, mu0=0.0005, mu_max=0.01), ())])
 def test_gsc_matches_oracle(mics, hop, kw, events):
