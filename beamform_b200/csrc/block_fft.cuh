@@ -12,6 +12,15 @@ namespace bf {
 
 constexpr int kGenThreads = 256;   // 8 warps x 255 registers: the radix-16 FP64 butterflies do not fit 128 registers (512 threads spilled 0.9 KB/thread)
 
+// sqrt through MUFU.SQRT (~2 ulp; NaN / negative / zero inputs behave as sqrtf).  The IEEE sqrtf is a ~10-instruction sequence
+// with a slow-path branch; the per-bin stages take 5-8 square roots per bin and none of them feeds an exact decision without a
+// guard band far wider than 2 ulp.
+__device__ __forceinline__ float sqrt_fast(float x) {
+  float r;
+  asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+
 // XOR swizzle of a transform's element index (elements are 8 or 16 bytes): the first Stockham pass scatters with a
 // stride of R elements, which without it lands every lane of a warp in the same shared-memory bank group.
 __device__ __forceinline__ int swz(int idx) { return idx ^ ((idx >> 4) & 7); }

@@ -294,7 +294,7 @@ __device__ __forceinline__ void phase_pair_fused(const KernelParams& p, int s, i
 #pragma unroll
       for (int i = 0; i < MM; i++) {
         const float2 xi = B.x[f][i];
-        if (i < M) magsum += sqrtf(fmaf(xi.x, xi.x, xi.y * xi.y));
+        if (i < M) magsum += sqrt_fast(fmaf(xi.x, xi.x, xi.y * xi.y));
         zr[i] = make_float2(xi.x * wst[i].x + xi.y * wst[i].y, xi.y * wst[i].x - xi.x * wst[i].y);   // conj(w) x
       }
       unsigned fl = 0;
@@ -383,12 +383,12 @@ __device__ __forceinline__ void phase_pair_fused(const KernelParams& p, int s, i
         Zs = p.mpf_alphaS * Zs + (1.0f - p.mpf_alphaS) * i2;   // phasempf.cpp:255-271
         rev0 = p.mpf_gamma * rev0 + p.mpf_rev_gain * s2;
         rev1 = p.mpf_gamma * rev1 + p.mpf_rev_gain * i2;
-        const float Lam = sqrtf(lam + p.mpf_eta * Zs + rev0 + rev1);
+        const float Lam = sqrt_fast(lam + p.mpf_eta * Zs + rev0 + rev1);
         float mag;
         if (p.out_only_noise) {
           mag = Lam * p.out_amp;
         } else {
-          mag = p.out_only_mcra ? (soi - sqrtf(lam)) * p.out_amp : (soi - Lam) * p.out_amp;
+          mag = p.out_only_mcra ? (soi - sqrt_fast(lam)) * p.out_amp : (soi - Lam) * p.out_amp;
           if (mag < 0.f) mag = p.noise_floor;
         }
         const float2 u2 = soi > 0.f ? unit : make_float2(1.f, 0.f);
@@ -1202,12 +1202,12 @@ __global__ void __launch_bounds__(kGenThreads, 1) frames_kernel_mcra(const __gri
         }
         S_prev = S;
         if (l > 0) {
-          const float mag_x = sqrtf(pq);
+          const float mag_x = sqrt_fast(pq);
           float mag;
           if (p.out_only_noise) {
-            mag = sqrtf(lam) * p.out_amp;
+            mag = sqrt_fast(lam) * p.out_amp;
           } else {
-            mag = (mag_x - sqrtf(lam)) * p.out_amp;
+            mag = (mag_x - sqrt_fast(lam)) * p.out_amp;
             if (mag < 0.f) mag = 0.f;
           }
           const float r0 = rsqrtf(pq);

@@ -61,9 +61,15 @@ __device__ __forceinline__ void mc_fft1024_fwd(float2 (&v)[32], float2* tile, co
   }
 }
 
+__device__ __forceinline__ float mc_sqrt(float x) {   // MUFU.SQRT; NaN and negative inputs behave as sqrtf
+  float r;
+  asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+
 // One bin, both frames of the pair: mcra.cpp:77-135 on the state the warp keeps in shared memory, then the bin's two cells of
-// G.  Out of line: the pair loop calls it 17 times with compile-time register rows; inlined, the loop body was 143 KB of SASS
-// and did not fit the instruction caches.  bk: bit0/1 window reset in frame 0/1, bit2/3 first window, bit4 frame t+1 exists.
+// G.  Inlined at its 17 call sites (compile-time register rows): as a real call it cost more than the instruction-cache misses
+// it saved (profiles/r02_experiments.md).  bk: bit0/1 window reset in frame 0/1, bit2/3 first window, bit4 frame t+1 exists.
 __device__ __forceinline__ void mcra_bin(const KernelParams& p, McWarp& my, int l, float2 x0, float2 x1, int bk, float inv_cl_0, float inv_cl_1) {
   constexpr int H = 512;
   const int nf = (bk & 16) ? 2 : 1;
@@ -90,21 +96,21 @@ __device__ __forceinline__ void mcra_bin(const KernelParams& p, McWarp& my, int 
     const float S = p.mcra_alphaS * S_prev + (1.0f - p.mcra_alphaS) * Sf;
     if (reset_f) { S_min = fminf(S_tmp, S); S_tmp = S; }
     else { S_min = fminf(S_min, S); S_tmp = fminf(S_tmp, S); }
-    if (fst_f || S < S_min * p.mcra_delta || lam > pq) {
-      if (fst_f && inv_cl_f > p.mcra_alphaD) lam = inv_cl_f * lam + (1.0f - inv_cl_f) * pq;
-      else lam = p.mcra_alphaD2 * lam + (1.0f - p.mcra_alphaD) * pq;
+    {   // branch-free: the three conditions differ from lane to lane
+      const bool upd = fst_f || S < S_min * p.mcra_delta || lam > pq;
+      const bool avg = fst_f && inv_cl_f > p.mcra_alphaD;
+      const float ca = avg ? inv_cl_f : p.mcra_alphaD2, cb = avg ? 1.0f - inv_cl_f : 1.0f - p.mcra_alphaD;
+      lam = upd ? ca * lam + cb * pq : lam;
     }
     S_prev = S;
     if (l > 0) {
-      const float mag_x = sqrtf(pq);
-      float mag;
-      if (p.out_only_noise) {
-        mag = sqrtf(lam) * p.out_amp;
-      } else {
-        mag = (mag_x - sqrtf(lam)) * p.out_amp;
-        if (mag < 0.f) mag = 0.f;
-      }
+      // |X| = pq * rsqrt(pq) and sqrt(lambda) through the MUFU approximations (~2 ulp): the IEEE square root is a 10-instruction
+      // sequence with a slow-path branch and was 13 % of the kernel's instructions
       const float r0 = rsqrtf(pq);
+      const float mag_x = pq == 0.f ? 0.f : pq * r0;   // NaN stays NaN
+      const float sl = mc_sqrt(lam);
+      float mag = p.out_only_noise ? sl * p.out_amp : (mag_x - sl) * p.out_amp;
+      if (!p.out_only_noise) mag = mag < 0.f ? 0.f : mag;   // (a NaN passes, as in mcra.cpp)
       const float2 unit = pq > 0.f ? make_float2(xf[f].x * r0, xf[f].y * r0) : make_float2(1.f, 0.f);   // e^{i arg X}
       yy[f] = make_float2(mag * unit.x, mag * unit.y);
     }

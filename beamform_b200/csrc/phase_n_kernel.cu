@@ -347,7 +347,7 @@ __global__ void __launch_bounds__(kGenThreads, CTAS) phase_n_kernel(const __grid
           for (int i = 0; i < MM; i++) {
             const float2 xi = x[f][i];
             const float n2 = fmaf(xi.x, xi.x, xi.y * xi.y);
-            ms += sqrtf(n2);
+            ms += sqrt_fast(n2);
             esum_dx += dx[i];
             guard += fminf(3.2f, fmaf(dx[i], rsqrtf(n2), 2.0e-6f));   // phase error bound of this microphone (n2 = 0 -> 3.2)
             zr[i] = make_float2(xi.x * wst[i].x + xi.y * wst[i].y, xi.y * wst[i].x - xi.x * wst[i].y);   // conj(w) x
@@ -361,7 +361,7 @@ __global__ void __launch_bounds__(kGenThreads, CTAS) phase_n_kernel(const __grid
             const float cc = zr[0].y * zr[1].x - zr[0].x * zr[1].y;
             const float q = sc.sin_thr * dd - sc.cos_thr * fabsf(cc);
             if (q > 0.f) b |= 2;
-            const float mod = sqrtf(fmaf(dd, dd, cc * cc));
+            const float mod = sqrt_fast(fmaf(dd, dd, cc * cc));
             d = !(fabsf(q) > (guard + 4.0e-6f) * mod);
           } else {
             float phi[MM];
@@ -462,12 +462,12 @@ __global__ void __launch_bounds__(kGenThreads, CTAS) phase_n_kernel(const __grid
             st7[4] = p.mpf_alphaS * st7[4] + (1.0f - p.mpf_alphaS) * i2;   // phasempf.cpp:255-271
             st7[5] = p.mpf_gamma * st7[5] + p.mpf_rev_gain * s2;
             st7[6] = p.mpf_gamma * st7[6] + p.mpf_rev_gain * i2;
-            const float Lam = sqrtf(st7[3] + p.mpf_eta * st7[4] + st7[5] + st7[6]);
+            const float Lam = sqrt_fast(st7[3] + p.mpf_eta * st7[4] + st7[5] + st7[6]);
             float mag;
             if (p.out_only_noise) {
               mag = Lam * p.out_amp;
             } else {
-              mag = p.out_only_mcra ? (soi - sqrtf(st7[3])) * p.out_amp : (soi - Lam) * p.out_amp;
+              mag = p.out_only_mcra ? (soi - sqrt_fast(st7[3])) * p.out_amp : (soi - Lam) * p.out_amp;
               if (mag < 0.f) mag = p.noise_floor;
             }
             const float2 u2 = soi > 0.f ? unit : make_float2(1.f, 0.f);

@@ -17,7 +17,7 @@ iID = hdr.index("ID")
 scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "ns": 1e-9, "us": 1e-6, "ms": 1e-3, "s": 1.0, "usecond": 1e-6, "msecond": 1e-3, "nsecond": 1e-9, "second": 1.0}
 per = defaultdict(dict)
 for r in rows[1:]:
-    if not any(k in r[iK] for k in ("bf::", "das_pairs_kernel", "sel_pairs_kernel", "sel_stream_kernel", "frames_kernel", "srp_", "save_prev_hop", "gss_reset", "zero_hops", "ref_kernel", "gsc_")):
+    if not any(k in r[iK] for k in ("bf::", "das_pairs_kernel", "sel_pairs_kernel", "sel_stream_kernel", "frames_kernel", "phase_n_kernel", "mcra_pairs_kernel", "srp_", "save_prev_hop", "gss_reset", "zero_hops", "ref_kernel", "gsc_")):
         continue
     per[(r[iID], r[iK])][r[iM]] = float(r[iV].replace(",", "")) * scale.get(r[iU], 1.0)
 # bench.py also launches a small selection-density probe (16 streams): only launches of at least half the kernel's longest
