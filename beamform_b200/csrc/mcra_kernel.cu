@@ -8,11 +8,13 @@
 // grid) and walks their frame pairs in order, the way das_pairs_kernel walks its range:
 //   1. hops t-1..t+1 of microphone 0 land in the warp's shared-memory tile (TMA bulk copy, mbarrier),
 //   2. window, pack z = 0.5 w (frame_t + i frame_{t+1}), warp-private 1024-point FFT (32 points per lane in registers),
-//   3. unpack by warp shuffles (Z[N-j] sits in lane (32-lane)%32, register 31-k2), |X|^2 of both frames to a
-//      shared-memory line so that the 3-tap smoothing reads its neighbours there,
+//   3. unpack by warp shuffles (Z[N-j] sits in lane (32-lane)%32, register 31-k2), |X|^2 of both frames to two lines in
+//      the (now idle) exchange tile so that the 3-tap smoothing reads its neighbours there,
 //   4. the MCRA recursion per bin on the 4 state scalars the warp keeps in shared memory for the whole stream,
-//      Y = max(0, |X| - sqrt(lambda)) out_amp e^{i arg X} -> G = Yh_t + i Yh_{t+1} assembled in the tile,
-//   5. inverse transform through the same code (IFFT(x) = swap(FFT(swap(x)))), synthesis window, overlap-add.
+//      Y = max(0, |X| - sqrt(lambda)) out_amp e^{i arg X} -> G = Yh_t + i Yh_{t+1} assembled IN PLACE in the spectrum
+//      registers (one shuffle hands G[N-l] to the partner lane),
+//   5. inverse transform through the same code (IFFT(x) = swap(FFT(swap(x)))), synthesis window, overlap-add with the
+//      tail in registers.
 // No block-level barrier after start-up; the state (mpf_state slots 0-3, layout shared with the CTA-per-stream kernel
 // frames_kernel_mcra) is read at the start of a launch and written back at its end.
 #include <cstdlib>
@@ -24,14 +26,12 @@
 
 namespace bf {
 
-constexpr int kMcWarps = 8;
+constexpr int kMcWarps = 8;   // 10 and 12 warps (204 / 168 registers) measured slower at the bench shape: whole streams are the unit of work, 2 368 streams = 2 per warp with 8
 constexpr int kMcLine = 17 * 32;   // bins 0..543 in (row k2, lane) order; rows 0..15 and bin 512 are the half spectrum
 
 struct McWarp {
-  float2 tile[1024];          // staged hops -> FFT exchange tile -> G
-  float psq[2][kMcLine];      // |X_f[j]|^2
+  float2 tile[1024];          // staged hops -> FFT exchange tile -> |X_f[j]|^2 lines (2 x kMcLine floats) -> exchange tile of the inverse
   float st[4][kMcLine];       // S_prev, S_tmp, S_min, lambda
-  float tail[512];
   uint64_t bar;
   uint64_t pad;
 };
@@ -70,7 +70,8 @@ __device__ __forceinline__ float mc_sqrt(float x) {   // MUFU.SQRT; NaN and nega
 // One bin, both frames of the pair: mcra.cpp:77-135 on the state the warp keeps in shared memory, then the bin's two cells of
 // G.  Inlined at its 17 call sites (compile-time register rows): as a real call it cost more than the instruction-cache misses
 // it saved (profiles/r02_experiments.md).  bk: bit0/1 window reset in frame 0/1, bit2/3 first window, bit4 frame t+1 exists.
-__device__ __forceinline__ void mcra_bin(const KernelParams& p, McWarp& my, int l, float2 x0, float2 x1, int bk, float inv_cl_0, float inv_cl_1) {
+__device__ __forceinline__ void mcra_bin(const KernelParams& p, McWarp& my, int l, float2 x0, float2 x1, int bk, float inv_cl_0, float inv_cl_1,
+                                         float2& g_lo, float2& g_hi) {
   constexpr int H = 512;
   const int nf = (bk & 16) ? 2 : 1;
   const float2 xf[2] = {x0, x1};
@@ -82,7 +83,7 @@ __device__ __forceinline__ void mcra_bin(const KernelParams& p, McWarp& my, int 
     const bool reset_f = (bk >> f) & 1;
     const float inv_cl_f = f ? inv_cl_1 : inv_cl_0;
     const int fst_f = (bk >> (2 + f)) & 1;
-    const float* ps = my.psq[f];
+    const float* ps = reinterpret_cast<const float*>(my.tile) + f * kMcLine;
     const float pq = ps[l];
     float Sf;
     if (l == 0) {
@@ -118,8 +119,8 @@ __device__ __forceinline__ void mcra_bin(const KernelParams& p, McWarp& my, int 
   my.st[0][l] = S_prev; my.st[1][l] = S_tmp; my.st[2][l] = S_min; my.st[3][l] = lam;
   float2 y0 = yy[0], y1 = yy[1];
   if (l == 0 || l == H) { y0.y = 0.f; y1.y = 0.f; }
-  my.tile[l] = make_float2(y0.x - y1.y, y0.y + y1.x);                          // Yh_t + i Yh_{t+1}
-  if (l > 0 && l < H) my.tile[1024 - l] = make_float2(y0.x + y1.y, y1.x - y0.y);   // conj(Yh_t) + i conj(Yh_{t+1})
+  g_lo = make_float2(y0.x - y1.y, y0.y + y1.x);   // G[l]     = Yh_t + i Yh_{t+1}
+  g_hi = make_float2(y0.x + y1.y, y1.x - y0.y);   // G[N - l] = conj(Yh_t) + i conj(Yh_{t+1})   (0 < l < N/2)
 }
 
 __global__ void __launch_bounds__(kMcWarps * 32, 1) mcra_pairs_kernel(const __grid_constant__ KernelParams p) {
@@ -170,8 +171,9 @@ __global__ void __launch_bounds__(kMcWarps * 32, 1) mcra_pairs_kernel(const __gr
 #pragma unroll
       for (int q = 0; q < 4; q++) my.st[q][j] = (j <= H) ? stg[q * L + j] : 0.f;
     }
+    float tail[16];   // OLA tail of the stream: sample 32 m2 + lane of the last frame's second half
 #pragma unroll
-    for (int m2 = 0; m2 < 16; m2++) my.tail[32 * m2 + lane] = p.tail[(size_t)s * H + 32 * m2 + lane];
+    for (int m2 = 0; m2 < 16; m2++) tail[m2] = p.tail[(size_t)s * H + 32 * m2 + lane];
     int cur_L = p.mcra_cur_L0, first_L = p.mcra_first0;
     __syncwarp();
 
@@ -180,9 +182,9 @@ __global__ void __launch_bounds__(kMcWarps * 32, 1) mcra_pairs_kernel(const __gr
       const int t = p.hop_begin + 2 * ip;
       const bool two = t + 1 < p.hop_end;
       // the forward and the inverse transform go through ONE call site (a rolled 2-trip loop): one copy of the butterfly code
+      float2 v[32];   // samples -> Z -> G (assembled in place) -> output samples
 #pragma unroll 1
       for (int dir = 0; dir < 2; dir++) {
-        float2 v[32];
         if (dir == 0) {
           const float* stage = reinterpret_cast<const float*>(my.tile);
           mbar_wait(&my.bar, job & 1);
@@ -196,10 +198,16 @@ __global__ void __launch_bounds__(kMcWarps * 32, 1) mcra_pairs_kernel(const __gr
             v[brev5(r + 16)] = make_float2(bb * w1, c * w1);
           });
         } else {
-          // inverse through the forward code: input rows with the parts swapped (stage 1 wants g[32 n1 + lane] in slot brev5(n1))
-          static_for<0, 32>([&](auto n1) {
-            const float2 g = my.tile[32 * n1 + lane];
-            v[brev5(n1)] = make_float2(g.y, g.x);
+          // inverse through the forward code: v[row] = G[32 row + lane]; stage 1 wants row n1 in slot brev5(n1), parts swapped
+          static_for<0, 32>([&](auto n1c) {
+            constexpr int n1 = decltype(n1c)::value, r = brev5(n1);
+            if constexpr (n1 < r) {
+              const float2 a = v[n1], b = v[r];
+              v[n1] = make_float2(b.y, b.x);
+              v[r] = make_float2(a.y, a.x);
+            } else if constexpr (n1 == r) {
+              v[n1] = make_float2(v[n1].y, v[n1].x);
+            }
           });
         }
         __syncwarp();   // staged samples / G consumed: the tile becomes the exchange buffer
@@ -222,12 +230,13 @@ __global__ void __launch_bounds__(kMcWarps * 32, 1) mcra_pairs_kernel(const __gr
             x0 = make_float2(a.x + b.x, a.y - b.y);
             x1 = make_float2(a.y + b.y, b.x - a.x);
           };
+          float* psq = reinterpret_cast<float*>(my.tile);   // the exchange step is over: the tile holds the two |X|^2 lines now
           static_for<0, 17>([&](auto k2c) {   // in_fft_square (mcra.cpp:73-76); row 16 = bins 512..543 (|X[512+i]| = |X[512-i]|)
             constexpr int k2 = decltype(k2c)::value;
             float2 x0, x1;
             unpack(k2c, x0, x1);
-            my.psq[0][32 * k2 + lane] = fmaf(x0.x, x0.x, x0.y * x0.y);
-            my.psq[1][32 * k2 + lane] = fmaf(x1.x, x1.x, x1.y * x1.y);
+            psq[32 * k2 + lane] = fmaf(x0.x, x0.x, x0.y * x0.y);
+            psq[kMcLine + 32 * k2 + lane] = fmaf(x1.x, x1.x, x1.y * x1.y);
           });
           __syncwarp();
           // window bookkeeping of the two frames (mcra.cpp:100-113), global per frame
@@ -244,12 +253,23 @@ __global__ void __launch_bounds__(kMcWarps * 32, 1) mcra_pairs_kernel(const __gr
             inv_cl_1 = 1.0f / (float)cur_L; fst_1 = first_L;
           }
           const int bk = (reset_0 ? 1 : 0) | (reset_1 ? 2 : 0) | (fst_0 ? 4 : 0) | (fst_1 ? 8 : 0) | (two ? 16 : 0);
+          // G is assembled IN PLACE in the spectrum registers: after its unpack, row k2 of a lane and row 31-k2 of its partner
+          // lane (lane 0: its own row 32-k2) are dead, and those are the cells G[l] and G[N-l] of the bins of this step
           static_for<0, 17>([&](auto k2c) {
             constexpr int k2 = decltype(k2c)::value;
             float2 x0, x1;
             unpack(k2c, x0, x1);                 // all lanes: the shuffles are warp-wide
-            if (k2 == 16 && lane != 0) return;   // only the Nyquist bin of row 16 is an output bin
-            mcra_bin(p, my, 32 * k2 + lane, x0, x1, bk, inv_cl_0, inv_cl_1);
+            float2 g_lo = make_float2(0.f, 0.f), g_hi = make_float2(0.f, 0.f);
+            if (k2 < 16 || lane == 0)            // only the Nyquist bin of row 16 is an output bin
+              mcra_bin(p, my, 32 * k2 + lane, x0, x1, bk, inv_cl_0, inv_cl_1, g_lo, g_hi);
+            if constexpr (k2 < 16) {
+              const float hx = __shfl_sync(0xffffffffu, g_hi.x, src_lane), hy = __shfl_sync(0xffffffffu, g_hi.y, src_lane);
+              v[k2] = g_lo;
+              if (lane != 0) v[31 - k2] = make_float2(hx, hy);
+              else if (k2 >= 1) v[32 - k2] = g_hi;
+            } else {
+              if (lane == 0) v[16] = g_lo;
+            }
           });
           __syncwarp();
         } else {
@@ -260,9 +280,9 @@ __global__ void __launch_bounds__(kMcWarps * 32, 1) mcra_pairs_kernel(const __gr
             const float w1 = win1024<m2 + 16>(s_o, c_o);
             const float y0a = v[m2].y * w0, y0b = v[m2 + 16].y * w1;   // frame t: first / second half
             const float y1a = v[m2].x * w0, y1b = v[m2 + 16].x * w1;   // frame t+1
-            o0[32 * m2 + lane] = my.tail[32 * m2 + lane] + y0a;
+            o0[32 * m2 + lane] = tail[m2] + y0a;
             if (two) o0[H + 32 * m2 + lane] = y0b + y1a;
-            my.tail[32 * m2 + lane] = two ? y1b : y0b;
+            tail[m2] = two ? y1b : y0b;
           });
         }
       }
@@ -273,7 +293,7 @@ __global__ void __launch_bounds__(kMcWarps * 32, 1) mcra_pairs_kernel(const __gr
       for (int q = 0; q < 4; q++) stg[q * L + j] = my.st[q][j];
     }
 #pragma unroll
-    for (int m2 = 0; m2 < 16; m2++) p.tail[(size_t)s * H + 32 * m2 + lane] = my.tail[32 * m2 + lane];
+    for (int m2 = 0; m2 < 16; m2++) p.tail[(size_t)s * H + 32 * m2 + lane] = tail[m2];
   }
 }
 
