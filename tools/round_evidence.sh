@@ -9,4 +9,5 @@ for w in mcra ref gsc ph c2hi; do
   timeout 400 python bench.py --workload $w --no-extra --steps 10 --warmup 3 > gpurun_out/${R}_bench_$w.json 2> gpurun_out/${R}_bench_$w.err
 done
 bash tools/profile_round.sh $R
+timeout 600 python tools/hop_latency.py > gpurun_out/${R}_hop_latency.json 2> gpurun_out/${R}_hop_latency.err
 ls -la gpurun_out | tail -40
