@@ -303,6 +303,65 @@ __device__ __forceinline__ float2 gss_item(const KernelParams& p, float2* Wg, si
   return y[0];
 }
 
+// The same update spread over a group of kGssGroup lanes (sel_pairs_kernel): the rows of W are independent once
+// sum_c |y_c|^2 is known, so lane g of the group takes rows g, g + kGssGroup, ... and the group shares the sum through two
+// shuffles.  A (bin, frame) item is one long dependent chain for a single thread and the solve phase of the kernel lasts as
+// long as one chain (profiles/r02_ncu_c3g.txt: half of the stall samples at the barrier behind it); the group shortens it
+// by the number of rows per lane.  `mask` names the lanes of the group (they all take the same branches).
+constexpr int kGssGroup = 4;
+template <int MAXC = kMaxC>
+__device__ __forceinline__ float2 gss_item_group(const KernelParams& p, float2* Wg, size_t ws, const float2* x, const float2* steer_l, int g, unsigned mask) {
+  const int C = p.C, M = p.M;
+  constexpr int kRows = (MAXC + kGssGroup - 1) / kGssGroup;
+  float2 y[kRows];
+  float alpha = 0.f;
+  for (int i = 0; i < M; i++) alpha += x[i].x * x[i].x + x[i].y * x[i].y;
+  alpha *= alpha;
+  float tot = 0.f;
+#pragma unroll
+  for (int k = 0; k < kRows; k++) {
+    const int c = g + k * kGssGroup;
+    float2 acc = make_float2(0.f, 0.f);
+    if (c < C)
+      for (int i = 0; i < M; i++) acc = cadd(acc, cmul(Wg[(size_t)(c * M + i) * ws], x[i]));
+    y[k] = acc;
+    tot += acc.x * acc.x + acc.y * acc.y;
+  }
+  // (E y)_r = sum_{c != r} y_r conj(y_c) y_c = y_r * (sum_c |y_c|^2 - |y_r|^2)   (gss.cpp:124-125)
+  tot += __shfl_xor_sync(mask, tot, 1);
+  tot += __shfl_xor_sync(mask, tot, 2);
+  const float s1 = (float)(4 * C) / alpha;   // gss.cpp:132
+#pragma unroll
+  for (int k = 0; k < kRows; k++) {
+    const int r = g + k * kGssGroup;
+    if (r >= C) break;
+    const float e = s1 * (tot - (y[k].x * y[k].x + y[k].y * y[k].y));
+    const float2 ey = make_float2(e * y[k].x, e * y[k].y);
+    float2 wa[MAXC];
+    if (p.gss_dj2_scale != 0.f) {   // (W A - I) row r; only K = 0 keeps the geometric term (gss.cpp:133, integer 1/(K+1))
+      for (int c = 0; c < C; c++) {
+        float2 acc = make_float2(c == r ? -1.f : 0.f, 0.f);
+        for (int i = 0; i < M; i++) acc = cadd(acc, cmul(Wg[(size_t)(r * M + i) * ws], steer_l[(size_t)c * M + i]));
+        wa[c] = acc;
+      }
+    }
+    for (int i = 0; i < M; i++) {
+      float2 dj = cmulc(ey, x[i]);   // dJ1(r,i) = (s1 (E y)_r) conj(x_i)
+      if (p.gss_dj2_scale != 0.f) {
+        float2 acc = make_float2(0.f, 0.f);
+        for (int c = 0; c < C; c++) acc = cadd(acc, cmulc(wa[c], steer_l[(size_t)c * M + i]));   // ((WA-I) A^H)(r,i)
+        dj.x += p.gss_dj2_scale * acc.x;
+        dj.y += p.gss_dj2_scale * acc.y;
+      }
+      float2 w = Wg[(size_t)(r * M + i) * ws];
+      w.x = p.lambda_mu * w.x - p.mu * dj.x;   // gss.cpp:136
+      w.y = p.lambda_mu * w.y - p.mu * dj.y;
+      Wg[(size_t)(r * M + i) * ws] = w;
+    }
+  }
+  return y[0];   // row 0 on lane 0 of the group
+}
+
 // FP64 re-decision of the magnitude gate for one (bin, frame): exact double DFT of that bin for every
 // microphone (util.h:235 windowing in double, mvdr.cpp:79-85 statistic), one warp per item.
 __device__ __forceinline__ bool gate_fp64(const KernelParams& p, int s, int t, int l, int f, int lane) {

@@ -423,7 +423,10 @@ __global__ void __launch_bounds__(kSelThreads, ALGO == ALGO_LCMV ? 1 : 2) sel_pa
     }
     // ------------------------------------------------------------------ B2: per-item solves
     if (live && ALGO == ALGO_GSS) {
-      for (int q = tid; q < sc.n_items; q += kSelThreads) {
+      // a group of kGssGroup lanes per selected bin (rows of W split over the lanes), both frames in turn (W carries over)
+      const int g = lane & (kGssGroup - 1);
+      const unsigned gmask = ((1u << kGssGroup) - 1u) << (lane & ~(kGssGroup - 1));
+      for (int q = tid / kGssGroup; q < sc.n_items; q += kSelThreads / kGssGroup) {
         const int l = sc.items[q] >> 1;
         const int slot = p.sel_slot[l];
         const float2* steer_l = p.steer + (size_t)l * p.C * M;
@@ -437,7 +440,9 @@ __global__ void __launch_bounds__(kSelThreads, ALGO == ALGO_LCMV ? 1 : 2) sel_pa
             if (ch < M) unpack2(ztiles + ch * 1024, l, a, b); else a = b = make_float2(0.f, 0.f);
             x[ch] = ff ? b : a;
           }
-          sc.y[ff][l] = gss_item(p, Wg, (size_t)p.Lsel, x, steer_l);
+          const float2 y0 = gss_item_group(p, Wg, (size_t)p.Lsel, x, steer_l, g, gmask);
+          if (g == 0) sc.y[ff][l] = y0;
+          __syncwarp(gmask);   // the group's W rows of frame t are written before frame t+1 reads them (same lanes own the same rows; kept for clarity)
         }
       }
     }
