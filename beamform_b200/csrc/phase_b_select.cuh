@@ -309,21 +309,42 @@ __device__ __forceinline__ float2 gss_item(const KernelParams& p, float2* Wg, si
 // long as one chain (profiles/r02_ncu_c3g.txt: half of the stall samples at the barrier behind it); the group shortens it
 // by the number of rows per lane.  `mask` names the lanes of the group (they all take the same branches).
 constexpr int kGssGroup = 4;
-template <int MAXC = kMaxC>
-__device__ __forceinline__ float2 gss_item_group(const KernelParams& p, float2* Wg, size_t ws, const float2* x, const float2* steer_l, int g, unsigned mask) {
+constexpr int kGssRows = (kMaxC + kGssGroup - 1) / kGssGroup;   // rows of W per lane
+
+// W rows of this lane for one bin, held in registers across the two frames of a pair (loaded once, stored once).
+struct GssRows {
+  float2 w[kGssRows][8];
+};
+__device__ __forceinline__ void gss_rows_load(const KernelParams& p, const float2* Wg, size_t ws, int g, GssRows& R) {
+#pragma unroll
+  for (int k = 0; k < kGssRows; k++) {
+    const int r = g + k * kGssGroup;
+#pragma unroll
+    for (int i = 0; i < 8; i++) R.w[k][i] = (r < p.C && i < p.M) ? Wg[(size_t)(r * p.M + i) * ws] : make_float2(0.f, 0.f);
+  }
+}
+__device__ __forceinline__ void gss_rows_store(const KernelParams& p, float2* Wg, size_t ws, int g, const GssRows& R) {
+#pragma unroll
+  for (int k = 0; k < kGssRows; k++) {
+    const int r = g + k * kGssGroup;
+#pragma unroll
+    for (int i = 0; i < 8; i++)
+      if (r < p.C && i < p.M) Wg[(size_t)(r * p.M + i) * ws] = R.w[k][i];
+  }
+}
+// gss.cpp:118-137 for one selected frame on the register-resident rows; x[i] = 0 for i >= M.  Returns y_0 on lane 0 of the group.
+__device__ __forceinline__ float2 gss_rows_step(const KernelParams& p, GssRows& R, const float2 (&x)[8], const float2* steer_l, int g, unsigned mask) {
   const int C = p.C, M = p.M;
-  constexpr int kRows = (MAXC + kGssGroup - 1) / kGssGroup;
-  float2 y[kRows];
+  float2 y[kGssRows];
   float alpha = 0.f;
   for (int i = 0; i < M; i++) alpha += x[i].x * x[i].x + x[i].y * x[i].y;
   alpha *= alpha;
   float tot = 0.f;
 #pragma unroll
-  for (int k = 0; k < kRows; k++) {
-    const int c = g + k * kGssGroup;
+  for (int k = 0; k < kGssRows; k++) {
     float2 acc = make_float2(0.f, 0.f);
-    if (c < C)
-      for (int i = 0; i < M; i++) acc = cadd(acc, cmul(Wg[(size_t)(c * M + i) * ws], x[i]));
+#pragma unroll
+    for (int i = 0; i < 8; i++) acc = cadd(acc, cmul(R.w[k][i], x[i]));   // rows >= C and columns >= M are zero
     y[k] = acc;
     tot += acc.x * acc.x + acc.y * acc.y;
   }
@@ -332,20 +353,24 @@ __device__ __forceinline__ float2 gss_item_group(const KernelParams& p, float2* 
   tot += __shfl_xor_sync(mask, tot, 2);
   const float s1 = (float)(4 * C) / alpha;   // gss.cpp:132
 #pragma unroll
-  for (int k = 0; k < kRows; k++) {
+  for (int k = 0; k < kGssRows; k++) {
     const int r = g + k * kGssGroup;
     if (r >= C) break;
     const float e = s1 * (tot - (y[k].x * y[k].x + y[k].y * y[k].y));
     const float2 ey = make_float2(e * y[k].x, e * y[k].y);
-    float2 wa[MAXC];
+    float2 wa[kMaxC];
     if (p.gss_dj2_scale != 0.f) {   // (W A - I) row r; only K = 0 keeps the geometric term (gss.cpp:133, integer 1/(K+1))
       for (int c = 0; c < C; c++) {
         float2 acc = make_float2(c == r ? -1.f : 0.f, 0.f);
-        for (int i = 0; i < M; i++) acc = cadd(acc, cmul(Wg[(size_t)(r * M + i) * ws], steer_l[(size_t)c * M + i]));
+#pragma unroll
+        for (int i = 0; i < 8; i++)
+          if (i < M) acc = cadd(acc, cmul(R.w[k][i], steer_l[(size_t)c * M + i]));
         wa[c] = acc;
       }
     }
-    for (int i = 0; i < M; i++) {
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      if (i >= M) break;
       float2 dj = cmulc(ey, x[i]);   // dJ1(r,i) = (s1 (E y)_r) conj(x_i)
       if (p.gss_dj2_scale != 0.f) {
         float2 acc = make_float2(0.f, 0.f);
@@ -353,13 +378,11 @@ __device__ __forceinline__ float2 gss_item_group(const KernelParams& p, float2* 
         dj.x += p.gss_dj2_scale * acc.x;
         dj.y += p.gss_dj2_scale * acc.y;
       }
-      float2 w = Wg[(size_t)(r * M + i) * ws];
-      w.x = p.lambda_mu * w.x - p.mu * dj.x;   // gss.cpp:136
-      w.y = p.lambda_mu * w.y - p.mu * dj.y;
-      Wg[(size_t)(r * M + i) * ws] = w;
+      R.w[k][i].x = p.lambda_mu * R.w[k][i].x - p.mu * dj.x;   // gss.cpp:136
+      R.w[k][i].y = p.lambda_mu * R.w[k][i].y - p.mu * dj.y;
     }
   }
-  return y[0];   // row 0 on lane 0 of the group
+  return y[0];
 }
 
 // FP64 re-decision of the magnitude gate for one (bin, frame): exact double DFT of that bin for every

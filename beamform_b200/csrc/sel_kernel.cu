@@ -431,6 +431,8 @@ __global__ void __launch_bounds__(kSelThreads, ALGO == ALGO_LCMV ? 1 : 2) sel_pa
         const int slot = p.sel_slot[l];
         const float2* steer_l = p.steer + (size_t)l * p.C * M;
         float2* Wg = p.gss_w + (size_t)s * BF_GSS_ROWS * M * p.Lsel + slot;   // [B][BF_GSS_ROWS][M][Lsel]
+        GssRows R;   // this lane's rows of W: loaded once, carried through both frames in registers, stored once
+        gss_rows_load(p, Wg, (size_t)p.Lsel, g, R);
         for (int ff = 0; ff < nf; ff++) {
           if (!sc.flag[ff][l]) continue;
           float2 x[8];
@@ -440,10 +442,10 @@ __global__ void __launch_bounds__(kSelThreads, ALGO == ALGO_LCMV ? 1 : 2) sel_pa
             if (ch < M) unpack2(ztiles + ch * 1024, l, a, b); else a = b = make_float2(0.f, 0.f);
             x[ch] = ff ? b : a;
           }
-          const float2 y0 = gss_item_group(p, Wg, (size_t)p.Lsel, x, steer_l, g, gmask);
+          const float2 y0 = gss_rows_step(p, R, x, steer_l, g, gmask);
           if (g == 0) sc.y[ff][l] = y0;
-          __syncwarp(gmask);   // the group's W rows of frame t are written before frame t+1 reads them (same lanes own the same rows; kept for clarity)
         }
+        gss_rows_store(p, Wg, (size_t)p.Lsel, g, R);
       }
     }
     if (live && ALGO != ALGO_GSS) {
