@@ -755,7 +755,7 @@ static int run_segment(bf_handle* h, const float* in, size_t ss, size_t ms, floa
   p.thr_mag = (float)(h->cfg.freq_mag_threshold * (double)h->M * (double)h->N);
   p.thr_mag_d = h->cfg.freq_mag_threshold;
   p.P = (int)h->cfg.past_windows;
-  { static const int dbg = getenv("BF_DEBUG") ? atoi(getenv("BF_DEBUG")) : 0; p.debug = dbg; }
+  { const char* dbg = getenv("BF_DEBUG"); p.debug = dbg ? atoi(dbg) : 0; }   // read per launch: tests switch it
   p.ring_depth = (int)h->cfg.past_windows + 2;
   p.ring_slot0 = (int)(h->frames_done % (uint64_t)p.ring_depth);
   p.hist = h->d_hist; p.sel_slot = h->d_sel_slot; p.sel_list = h->d_sel_list; p.Lsel = h->Lsel;

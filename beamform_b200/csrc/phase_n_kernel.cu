@@ -401,11 +401,15 @@ __global__ void __launch_bounds__(kGenThreads, CTAS) phase_n_kernel(const __grid
                 if (sc.list[q] == key) { fl[f] = sc.res[q]; doubt[f] = false; break; }
             }
           } else {
-#pragma unroll
-            for (int f = 0; f < 2; f++) {
-              if (!doubt[f]) continue;
-              const int q = atomicAdd(&sc.n_list, 1);
-              if (q < kPhnList) sc.list[q] = (unsigned short)(l * 2 + f);   // else: a later round
+            // all-or-nothing: a bin that needs both frames takes two adjacent slots or none.  (Taken one by one, an overflowing
+            // round hands every slot to the first frames of the first warps, no bin ever gets both, and the pair never ends.)
+            const int cnt = (doubt[0] ? 1 : 0) + (doubt[1] ? 1 : 0);
+            int q = atomicAdd(&sc.n_list, cnt);
+            if (q + cnt <= kPhnList) {   // else: a later round
+              if (doubt[0]) sc.list[q++] = (unsigned short)(l * 2);
+              if (doubt[1]) sc.list[q] = (unsigned short)(l * 2 + 1);
+            } else if (q < kPhnList) {
+              sc.list[q] = (unsigned short)(l * 2);   // the one slot a refused pair leaves behind: a valid key, so the round decides it (unused)
             }
           }
           if (doubt[0] || doubt[1]) continue;   // stays pending
@@ -541,7 +545,7 @@ __global__ void __launch_bounds__(kGenThreads, CTAS) phase_n_kernel(const __grid
     }
     __syncthreads();
   }
-  if (p.debug == 3 && blockIdx.x < 4 && tid == 0) printf("phase_n_kernel: stream %d: %d exact re-decisions over %d pairs\n", s, n_recheck, npairs);
+  if ((p.debug == 3 || (p.debug >= 1000 && p.debug % 1000 == 3)) && blockIdx.x < 4 && tid == 0) printf("phase_n_kernel: stream %d: %d exact re-decisions over %d pairs\n", s, n_recheck, npairs);
   for (int i = tid; i < H; i += kGenThreads) p.tail[(size_t)s * H + i] = sc.tail[i];
   if (kMpf)
     for (int i = tid; i < p.smooth_size - 1; i += kGenThreads) p.smooth_hist[(size_t)s * 64 + i] = sc.hist[i];

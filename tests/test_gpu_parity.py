@@ -313,6 +313,38 @@ def test_phase_kernels_both_precisions(monkeypatch, env, algo, mics, hop, kw):
     assert mism <= MASK_MISMATCH_FRAC * msk.size
 
 
+@pytest.mark.parametrize("algo,mics,hop,kw", [("phasempf", "binaural", 2048, {}), ("phase", "aira3", 512, dict(mag_threshold=0.002)),
+                                              ("phasempf", "aira3", 256, {}), ("phase", "binaural", 1024, dict(mag_threshold=0.002))])
+@pytest.mark.timeout(180, method="thread")
+def test_phase_fp32_kernel_with_every_significant_bin_re_decided(monkeypatch, capfd, algo, mics, hop, kw):
+    """Stress of phase_n_kernel's deferred exact decisions: with the error bound blown up 10 000x (BF_DEBUG=100003: kappa = 1e-2) most
+    significant bins of every frame are doubtful (a value ending in 003 also prints the count), the list of 160 items overflows and a pair takes several collect / decide / apply
+    rounds (the pseudo-bin and the bin it folds into wait for each other).  Every decision is then the exact one, so masks and output
+    must still match the oracle; streams are cut into calls of odd lengths."""
+    monkeypatch.setenv("BF_PHASE_F32", "1")
+    monkeypatch.setenv("BF_DEBUG", "100003")
+    cfg = bf.make_config(algo, mics=mics, hop=hop, initial_angle=15.0, **kw)
+    n_hops = 23
+    x = np.stack([synth_stream(bf.GEOMETRIES[mics], n_hops * hop, seed=760 + b, gate_hz=1.3 if algo == "phasempf" else 0.0) for b in range(3)])
+    ref, _, msk = oracle_with_flags(cfg, x)
+    b = bf.Beamformer(cfg, n_streams=3)
+    cuts = [0, 7 * hop, 8 * hop, 15 * hop, n_hops * hop]
+    got = np.concatenate([b.process(x[:, :, a:c]) for a, c in zip(cuts[:-1], cuts[1:])], axis=1)
+    err = rel_l2(got, ref)
+    got1, flags, _ = run_device(cfg, x, H=hop)
+    kept = (flags >> 1) & 1
+    mism = int((kept != msk).sum())
+    print(algo, mics, "hop", hop, "rel_l2", err, "single call", rel_l2(got1, ref), "mask mismatches", mism, "of", msk.size)
+    assert err <= REL_L2_TOL and rel_l2(got1, ref) <= REL_L2_TOL
+    assert mism <= MASK_MISMATCH_FRAC * msk.size
+    import re
+    import torch
+    torch.cuda.synchronize()
+    counts = [(int(m.group(1)), int(m.group(2))) for m in re.finditer(r"(\d+) exact re-decisions over (\d+) pairs", capfd.readouterr().out)]
+    assert counts, "the kernel under test must be phase_n_kernel"
+    assert max(c / max(n, 1) for c, n in counts) > 160, "the stress must overflow the list of a round: %r" % (counts,)
+
+
 @pytest.mark.parametrize("algo,mics,hop,interf,events", [
     ("mvdr", "circ8", 1024, (), ()), ("mvdr", "aira3", 256, (), ()), ("mvdr", "circ12", 512, (), ()), ("mvdr", "circ16", 512, (), ()),
     ("lcmv", "circ8", 256, (80.0, -60.0, 150.0), ((15, "theta", 20.0), (25, "interf", 2, -55.0), (35, "interf", 4, 120.0), (45, "interf", 1, 119.5))),
