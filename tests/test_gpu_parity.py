@@ -195,6 +195,24 @@ def test_gss_with_events_matches_oracle():
     assert err <= REL_L2_TOL
 
 
+@pytest.mark.parametrize("mics,interf", [("circ8", (70.0,)), ("circ8", (70.0, -110.0)), ("aira3", (80.0, -60.0)), ("circ8", (40.0, 80.0, 120.0, 160.0, -150.0, -100.0)),
+                                         ("circ8", (40.0, 80.0, 120.0, 160.0, -150.0, -100.0, -50.0))])
+def test_gss_row_groups_every_constraint_count(mics, interf):
+    """sel_pairs_kernel<gss> splits the rows of the separation matrix over groups of 4 lanes (1 or 2 rows per lane): 2, 3, 7 and 8
+    rows here (1 and 4-5 rows are in the neighbouring tests), state carried across calls of odd lengths."""
+    kw = dict(mu=1e-4) if len(interf) > 4 else {}   # many rows: a smaller step keeps the recursion well away from divergence
+    cfg = bf.make_config("gss", mics=mics, initial_angle=5.0, interferers=interf, **kw)
+    x = synth_batch(bf.GEOMETRIES[mics], 3, 61 * H, seed=47)
+    ref, sel, _ = oracle_with_flags(cfg, x)
+    b = bf.Beamformer(cfg, n_streams=3)
+    cuts = [0, 9 * H, 10 * H, 33 * H, 61 * H]
+    got = np.concatenate([b.process(x[:, :, a:c]) for a, c in zip(cuts[:-1], cuts[1:])], axis=1)
+    err = finite_rel_l2(got, ref)
+    print("gss", mics, len(interf) + 1, "rows rel_l2", err, "selected fraction", sel.mean())
+    assert sel.sum() > 500
+    assert err <= REL_L2_TOL
+
+
 def test_gss_without_interferers_keeps_geometric_gradient():
     # K = 0: the integer 1/(K+1) is 1, so dJ2 is active (SURVEY B-7)
     cfg = bf.make_config("gss", mics="aira3", initial_angle=10.0)
