@@ -10,7 +10,7 @@
 
 namespace bf {
 
-constexpr int kGenThreads = 256;   // 8 warps x 255 registers: the radix-16 FP64 butterflies do not fit 128 registers (512 threads spilled 0.9 KB/thread)
+constexpr int kGenThreads = 256;   // default CTA size of the CTA-per-stream kernels (the in-place passes take the actual size as template argument T)
 
 // sqrt through MUFU.SQRT (~2 ulp; NaN / negative / zero inputs behave as sqrtf).  The IEEE sqrtf is a ~10-instruction sequence
 // with a slow-path branch; the per-bin stages take 5-8 square roots per bin and none of them feeds an exact decision without a
@@ -100,8 +100,9 @@ struct Step {
 
 // n_pass in-place passes of radix R, Ns = 1 << sh0, then * R per pass, over nfft transforms stored back to back.
 // Every read of a round precedes every write: two block barriers per round.
-template <int NN, int R, int DIR, typename V>
+template <int NN, int R, int DIR, typename V, int T = 256>
 __device__ __forceinline__ void passes_inplace(V* z, int nfft, const V* __restrict__ tw, int tid, int sh0, int n_pass) {
+  constexpr int kGenThreads = T;   // threads of the CTA (shadows the default)
   typedef Step<NN, R, DIR, V> S;
   constexpr int per = S::per;
   constexpr int g = kGenThreads / per > 0 ? kGenThreads / per : 1;   // transforms per round
@@ -122,19 +123,19 @@ __device__ __forceinline__ void passes_inplace(V* z, int nfft, const V* __restri
   }
 }
 
-template <int NN, int DIR, typename V>
+template <int NN, int DIR, typename V, int T = 256>
 __device__ __forceinline__ void block_fft(V* z, int nfft, const V* __restrict__ tw, int tid) {
   if constexpr (NN == 4096) {
-    passes_inplace<NN, 16, DIR, V>(z, nfft, tw, tid, 0, 3);
+    passes_inplace<NN, 16, DIR, V, T>(z, nfft, tw, tid, 0, 3);
   } else if constexpr (NN == 2048) {
-    passes_inplace<NN, 16, DIR, V>(z, nfft, tw, tid, 0, 2);
-    passes_inplace<NN, 8, DIR, V>(z, nfft, tw, tid, 8, 1);
+    passes_inplace<NN, 16, DIR, V, T>(z, nfft, tw, tid, 0, 2);
+    passes_inplace<NN, 8, DIR, V, T>(z, nfft, tw, tid, 8, 1);
   } else if constexpr (NN == 1024) {
-    passes_inplace<NN, 16, DIR, V>(z, nfft, tw, tid, 0, 1);
-    passes_inplace<NN, 8, DIR, V>(z, nfft, tw, tid, 4, 2);
+    passes_inplace<NN, 16, DIR, V, T>(z, nfft, tw, tid, 0, 1);
+    passes_inplace<NN, 8, DIR, V, T>(z, nfft, tw, tid, 4, 2);
   } else {
     static_assert(NN == 512, "supported frame sizes: 512, 1024, 2048, 4096");
-    passes_inplace<NN, 8, DIR, V>(z, nfft, tw, tid, 0, 3);
+    passes_inplace<NN, 8, DIR, V, T>(z, nfft, tw, tid, 0, 3);
   }
 }
 
@@ -178,9 +179,9 @@ __device__ __forceinline__ V* block_fft_oop(V* a, V* b, const V* __restrict__ tw
 // shared-memory window, so the accesses stay LDS/STS.
 extern __shared__ __align__(16) unsigned char gen_smem_raw[];
 
-template <int NN, int DIR, typename V>
+template <int NN, int DIR, typename V, int T = 256>
 __device__ __noinline__ void block_fft_fn(unsigned z_off, int nfft, const V* __restrict__ tw, int tid) {
-  block_fft<NN, DIR, V>(reinterpret_cast<V*>(gen_smem_raw + z_off), nfft, tw, tid);
+  block_fft<NN, DIR, V, T>(reinterpret_cast<V*>(gen_smem_raw + z_off), nfft, tw, tid);
 }
 // returns the byte offset of the buffer that holds the result
 template <int NN, int DIR, typename V>

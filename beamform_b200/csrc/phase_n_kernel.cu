@@ -33,8 +33,9 @@ constexpr float kFftErrRel = 4.0e-7f; // * |Z[k]| of the output itself
 
 constexpr int kPhnList = 160;   // exact re-decisions per round (a pair with more takes further rounds)
 
-template <int NN>
+template <int NN, int T>
 struct PhnScratch {
+  static constexpr int kGenThreads = T;
   float tail[NN / 2];
   float hist[64];                       // phasempf smoother: the last smooth_size-1 OLA samples
   float epart[kGenThreads / 32][4];     // per-warp partial energies of the packed frame pair, per microphone
@@ -54,8 +55,9 @@ struct PhnScratch {
 //   X[j] = sum_{n'} W^{j n'} (x[n'] w[n'] + (-1)^j x[n'+H] w[n'+H]),   W^{j n'} = W^{j tid} W^{256 j i},  n' = tid + 256 i:
 // one gathered twiddle per thread and item and H/256 that are the same for every thread.
 // Flag bits: bit0 = magnitude gate passed, bit1 = phases agree.
-template <int NN, int MM>
-__device__ __noinline__ void phn_decide_exact(const KernelParams& p, PhnScratch<NN>& sc, int s, int t, bool two, int n_items, bool use_gate) {
+template <int NN, int MM, int T>
+__device__ __noinline__ void phn_decide_exact(const KernelParams& p, PhnScratch<NN, T>& sc, int s, int t, bool two, int n_items, bool use_gate) {
+  constexpr int kGenThreads = T;   // threads of the CTA (shadows the default)
   constexpr int H = NN / 2, L = NN / 2 + 2, W = kGenThreads / 32;
   constexpr int B = MM == 2 ? 4 : 2;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -159,15 +161,16 @@ __device__ __forceinline__ float phn_wrap_diff(float a, float b) {   // phase.cp
   return d > 3.14159265358979f ? 6.28318530717959f - d : d;
 }
 
-template <int ALGO, int NN, int MM, int CTAS>
-__global__ void __launch_bounds__(kGenThreads, CTAS) phase_n_kernel(const __grid_constant__ KernelParams p) {
+template <int ALGO, int NN, int MM, int T, int CTAS>
+__global__ void __launch_bounds__(T, CTAS) phase_n_kernel(const __grid_constant__ KernelParams p) {
+  constexpr int kGenThreads = T;   // threads of the CTA (shadows the default)
   constexpr int H = NN / 2, L = NN / 2 + 2;
   constexpr bool kGate = (ALGO == ALGO_PHASE);
   constexpr bool kMpf = (ALGO == ALGO_PHASEMPF);
   constexpr int kIter = (H + kGenThreads - 1) / kGenThreads;
   static_assert(H % kGenThreads == 0, "every thread owns the same number of bins");
   float2* zall = reinterpret_cast<float2*>(gen_smem_raw);   // [MM][NN]
-  PhnScratch<NN>& sc = *reinterpret_cast<PhnScratch<NN>*>(zall + (size_t)MM * NN);
+  PhnScratch<NN, T>& sc = *reinterpret_cast<PhnScratch<NN, T>*>(zall + (size_t)MM * NN);
   const unsigned t1_off = (unsigned)(NN * sizeof(float2));
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int s = blockIdx.x + p.stream_begin;
@@ -244,7 +247,7 @@ __global__ void __launch_bounds__(kGenThreads, CTAS) phase_n_kernel(const __grid
     }
     __syncthreads();
     if (tid == 0) sc.n_list = 0;   // published by the transform's own barriers
-    block_fft_fn<NN, -1, float2>(0u, MM, tw, tid);
+    block_fft_fn<NN, -1, float2, T>(0u, MM, tw, tid);
     {   // error bound of this pair's transforms: needs ||z||_2 (pack) and max |Z| (here)
       float zm[MM];
 #pragma unroll
@@ -504,7 +507,7 @@ __global__ void __launch_bounds__(kGenThreads, CTAS) phase_n_kernel(const __grid
         __syncthreads();
       } else {
         const int n_items = min(sc.n_list, kPhnList);
-        phn_decide_exact<NN, MM>(p, sc, s, t, two, n_items, kGate);
+        phn_decide_exact<NN, MM, T>(p, sc, s, t, two, n_items, kGate);
         n_recheck += n_items;
         apply = true;
       }
@@ -551,17 +554,37 @@ __global__ void __launch_bounds__(kGenThreads, CTAS) phase_n_kernel(const __grid
     for (int i = tid; i < p.smooth_size - 1; i += kGenThreads) p.smooth_hist[(size_t)s * 64 + i] = sc.hist[i];
 }
 
-template <int NN>
-static size_t phn_smem(int M) { return sizeof(float2) * (size_t)M * NN + sizeof(PhnScratch<NN>) + 16; }
+template <int NN, int T>
+static size_t phn_smem(int M) { return sizeof(float2) * (size_t)M * NN + sizeof(PhnScratch<NN, T>) + 16; }
 
 template <int ALGO, int NN, int MM>
 static cudaError_t launch_phn(const KernelParams& p, cudaStream_t st) {
-  const size_t smem = phn_smem<NN>(MM);
-  static const int ctas = getenv("BF_PHN_CTAS") ? atoi(getenv("BF_PHN_CTAS")) : 3;   // tuning: registers per thread 80 (3 CTAs per SM) or 128 (2)
-  void (*k)(KernelParams) = ctas == 2 ? phase_n_kernel<ALGO, NN, MM, 2> : phase_n_kernel<ALGO, NN, MM, 3>;
+  // CTA size and CTAs per SM.  Up to 1024 points: 128 threads x 4 CTAs at 128 registers (a 1024-point transform is 64 radix-16 / 128
+  // radix-8 tasks, the warp that carries the pseudo-bin delays 4 warps instead of 8, and the per-bin stage does not spill; measured on
+  // the 3-microphone phase node: 256 x 3 at 80 registers 5.54 ms, 128 x 6 at 80 registers 5.33 ms, 128 x 4 at 128 registers 4.22 ms).
+  // Longer frames: 256 threads x 3 CTAs (the shared memory allows no more; 80 registers).  BF_PHN_T / BF_PHN_CTAS override (tuning).
+  const char* e_t = getenv("BF_PHN_T");
+  const char* e_c = getenv("BF_PHN_CTAS");
+  const int threads = e_t ? atoi(e_t) : (NN <= 1024 ? 128 : 256);
+  const int ctas = e_c ? atoi(e_c) : 0;
+  void (*k)(KernelParams) = nullptr;
+  size_t smem = 0;
+  int nthreads = 0;
+  if constexpr (NN <= 1024) {
+    if (threads == 128) {
+      k = ctas == 6 ? phase_n_kernel<ALGO, NN, MM, 128, 6> : ctas == 3 ? phase_n_kernel<ALGO, NN, MM, 128, 3> : phase_n_kernel<ALGO, NN, MM, 128, 4>;
+      smem = phn_smem<NN, 128>(MM);
+      nthreads = 128;
+    }
+  }
+  if (!k) {
+    k = ctas == 2 ? phase_n_kernel<ALGO, NN, MM, 256, 2> : phase_n_kernel<ALGO, NN, MM, 256, 3>;
+    smem = phn_smem<NN, 256>(MM);
+    nthreads = 256;
+  }
   cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  k<<<p.n_streams, kGenThreads, smem, st>>>(p);
+  k<<<p.n_streams, nthreads, smem, st>>>(p);
   return cudaGetLastError();
 }
 template <int ALGO, int NN>
