@@ -156,6 +156,30 @@ __device__ __noinline__ void phn_decide_exact(const KernelParams& p, PhnScratch<
   }
 }
 
+// atan2 in ~22 instructions (atan2f: 53 per call, 19 % of the kernel's samples with three microphones): odd minimax polynomial of
+// degree 15 on [0, 1] (max error 1.3e-7 evaluated in FP32) + octant folding; with the approximate division the absolute error stays
+// below 4e-7 rad, which the decision's guard band carries (3e-6 below).  NaN in, NaN out, like atan2f.
+__device__ __forceinline__ float phn_atan2(float y, float x) {
+  const float ax = fabsf(x), ay = fabsf(y);
+  const float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
+  const float a = mx > 0.f ? __fdividef(mn, mx) : 0.f;   // atan2(0, 0) = 0
+  const float s = a * a;
+  float q = -0.004054515156894922f;
+  q = fmaf(q, s, 0.021862763911485672f);
+  q = fmaf(q, s, -0.055912040174007416f);
+  q = fmaf(q, s, 0.0964217558503151f);
+  q = fmaf(q, s, -0.13908620178699493f);
+  q = fmaf(q, s, 0.19946563243865967f);
+  q = fmaf(q, s, -0.33329859375953674f);
+  q = fmaf(q, s, 0.9999993443489075f);
+  float r = q * a;
+  r = ay > ax ? 1.57079632679489662f - r : r;
+  r = x < 0.f ? 3.14159265358979324f - r : r;
+  const float t = x + y;
+  r = (t != t) ? t : r;
+  return copysignf(r, y);
+}
+
 __device__ __forceinline__ float phn_wrap_diff(float a, float b) {   // phase.cpp:58-60
   const float d = fabsf(a - b);
   return d > 3.14159265358979f ? 6.28318530717959f - d : d;
@@ -369,7 +393,7 @@ __global__ void __launch_bounds__(T, CTAS) phase_n_kernel(const __grid_constant_
           } else {
             float phi[MM];
 #pragma unroll
-            for (int i = 0; i < MM; i++) phi[i] = atan2f(zr[i].y, zr[i].x);
+            for (int i = 0; i < MM; i++) phi[i] = phn_atan2(zr[i].y, zr[i].x);
             float tot = 0.f;
 #pragma unroll
             for (int a = MM - 2; a >= 0; a--) {
@@ -380,7 +404,7 @@ __global__ void __launch_bounds__(T, CTAS) phase_n_kernel(const __grid_constant_
             }
             const float mean_diff = tot / (float)(MM * (MM - 1) / 2);
             if (mean_diff < p.min_phase_rad) b |= 2;
-            d = !(fabsf(mean_diff - p.min_phase_rad) > guard * (2.0f / (float)MM) + 2.0e-6f);
+            d = !(fabsf(mean_diff - p.min_phase_rad) > guard * (2.0f / (float)MM) + 3.0e-6f);
           }
           const float e_all = sc.e_all;
           d = d && ms > 1.0e-4f * e_all;   // only bins that matter
