@@ -1495,7 +1495,7 @@ __global__ void __launch_bounds__(kNlmsWarps * 32) gsc_nlms_kernel(const __grid_
 // computed once per sample, and the 2(M-1) sums of a sample reduced by one interleaved butterfly.  Same arithmetic per
 // element and the same state layout as gsc_nlms_kernel.
 template <int MC>
-__global__ void __launch_bounds__(kNlmsWarps * 32) gsc_nlms_fast_kernel(const __grid_constant__ KernelParams p) {
+__global__ void __launch_bounds__(kNlmsWarps * 32, 8) gsc_nlms_fast_kernel(const __grid_constant__ KernelParams p) {
   constexpr int F = 128, Q = 4, M = MC + 1;
   extern __shared__ __align__(16) float nlms_smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
