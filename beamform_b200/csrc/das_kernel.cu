@@ -29,36 +29,7 @@ namespace bf {
 
 constexpr int kTileF2 = 1024;   // float2 per warp tile (8 KB, XOR-swizzled: no padding)
 
-// Forward 1024-point FFT with an 8 KB swizzled exchange tile.  Element (row k1, col c) lives at float2 index
-// k1*32 + (c ^ ((k1 & 15) << 1)): row stores are full 256-byte rows, column loads are LDS.128 whose eight
-// lanes per phase fall into distinct 16-byte bank groups.
-// The two 32-point register passes share ONE copy of the butterfly code (rolled 2-trip loop): the fused kernel's
-// hot loop then fits the SM's instruction caches (a fully inlined forward+inverse pair was 85 KB of SASS and the
-// warps stalled on instruction fetch).  The inverse transform reuses this code through
-// IFFT(x) = swap(FFT(swap(x))), swap = exchange of real and imaginary parts (a register renaming).
-template <class F>
-__device__ __forceinline__ void warp_fft1024_fwd(float2 (&v)[32], float2* tile, const float2* __restrict__ tw, int lane, F&& after_exchange) {
-#pragma unroll 1
-  for (int pass = 0; pass < 2; pass++) {
-    fft_dit<32, -1>(v);
-    if (pass == 0) {
-#pragma unroll
-      for (int k1 = 1; k1 < 32; k1++) v[k1] = cmul(v[k1], tw[k1 * 32 + lane]);
-#pragma unroll
-      for (int k1 = 0; k1 < 32; k1++) tile[k1 * 32 + (lane ^ ((k1 & 15) << 1))] = v[k1];
-      __syncwarp();
-      const float4* row = reinterpret_cast<const float4*>(tile + lane * 32);
-      const int sw = lane & 15;
-      static_for<0, 16>([&](auto q) {
-        const float4 r = row[q ^ sw];
-        v[brev5(2 * q)] = make_float2(r.x, r.y);
-        v[brev5(2 * q + 1)] = make_float2(r.z, r.w);
-      });
-      __syncwarp();
-      after_exchange();   // the tile is free from here until the next job reads its staged hops
-    }
-  }
-}
+// (the transform itself is warp_fft1024_fwd in warp_fft1024.cuh)
 
 struct PairPos {
   int s;      // stream (global index)

@@ -36,30 +36,6 @@ struct McWarp {
   uint64_t pad;
 };
 
-// forward transform of das_kernel.cu (same exchange-tile layout), repeated here because that one lives in its .cu file
-template <class F>
-__device__ __forceinline__ void mc_fft1024_fwd(float2 (&v)[32], float2* tile, const float2* __restrict__ tw, int lane, F&& after_exchange) {
-#pragma unroll 1
-  for (int pass = 0; pass < 2; pass++) {
-    fft_dit<32, -1>(v);
-    if (pass == 0) {
-#pragma unroll
-      for (int k1 = 1; k1 < 32; k1++) v[k1] = cmul(v[k1], tw[k1 * 32 + lane]);
-#pragma unroll
-      for (int k1 = 0; k1 < 32; k1++) tile[k1 * 32 + (lane ^ ((k1 & 15) << 1))] = v[k1];
-      __syncwarp();
-      const float4* row = reinterpret_cast<const float4*>(tile + lane * 32);
-      const int sw = lane & 15;
-      static_for<0, 16>([&](auto q) {
-        const float4 r = row[q ^ sw];
-        v[brev5(2 * q)] = make_float2(r.x, r.y);
-        v[brev5(2 * q + 1)] = make_float2(r.z, r.w);
-      });
-      __syncwarp();
-      after_exchange();
-    }
-  }
-}
 
 __device__ __forceinline__ float mc_sqrt(float x) {   // MUFU.SQRT; NaN and negative inputs behave as sqrtf
   float r;
@@ -211,7 +187,7 @@ __global__ void __launch_bounds__(kMcWarps * 32, 1) mcra_pairs_kernel(const __gr
           });
         }
         __syncwarp();   // staged samples / G consumed: the tile becomes the exchange buffer
-        mc_fft1024_fwd(v, my.tile, tw, lane, [&]() {
+        warp_fft1024_fwd(v, my.tile, tw, lane, [&]() {
           if (dir == 1 && ip + 1 < npairs) {   // the tile is free: the next pair's hops may land
             fence_proxy_async();
             issue(s, t + 2, t + 3 < p.hop_end);

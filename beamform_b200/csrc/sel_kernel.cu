@@ -34,28 +34,6 @@ namespace bf {
 constexpr int kSelWarps = 8;
 constexpr int kSelThreads = kSelWarps * 32;
 
-// forward 1024-point FFT, same compact form as das_kernel.cu (one copy of the butterfly code, swizzled 8 KB tile)
-__device__ __forceinline__ void sel_fft1024_fwd(float2 (&v)[32], float2* tile, const float2* __restrict__ tw, int lane) {
-#pragma unroll 1
-  for (int pass = 0; pass < 2; pass++) {
-    fft_dit<32, -1>(v);
-    if (pass == 0) {
-#pragma unroll
-      for (int k1 = 1; k1 < 32; k1++) v[k1] = cmul(v[k1], tw[k1 * 32 + lane]);
-#pragma unroll
-      for (int k1 = 0; k1 < 32; k1++) tile[k1 * 32 + (lane ^ ((k1 & 15) << 1))] = v[k1];
-      __syncwarp();
-      const float4* row = reinterpret_cast<const float4*>(tile + lane * 32);
-      const int sw = lane & 15;
-      static_for<0, 16>([&](auto q) {
-        const float4 r = row[q ^ sw];
-        v[brev5(2 * q)] = make_float2(r.x, r.y);
-        v[brev5(2 * q + 1)] = make_float2(r.z, r.w);
-      });
-      __syncwarp();
-    }
-  }
-}
 
 struct SelShared {
   float2 y[2][kL1K];
@@ -300,7 +278,7 @@ __global__ void __launch_bounds__(kSelThreads, ALGO == ALGO_LCMV ? 1 : 2) sel_pa
         for (int o = 16; o > 0; o >>= 1) { e0 += __shfl_xor_sync(0xffffffffu, e0, o); e1 += __shfl_xor_sync(0xffffffffu, e1, o); }
         if (lane == 0) { sc.sqrtE[0][warp] = 2.0f * sqrtf(e0); sc.sqrtE[1][warp] = 2.0f * sqrtf(e1); }
       }
-      sel_fft1024_fwd(v, myz, tw, lane);
+      warp_fft1024_fwd(v, myz, tw, lane);
 #pragma unroll
       for (int k2 = 0; k2 < 32; k2++) myz[k2 * 32 + lane] = v[k2];
     }
@@ -405,7 +383,7 @@ __global__ void __launch_bounds__(kSelThreads, ALGO == ALGO_LCMV ? 1 : 2) sel_pa
       float2 v[32];
       static_for<0, 32>([&](auto n1) { const float2 gg = sc.g[n1 * 32 + lane]; v[brev5(n1)] = make_float2(gg.y, gg.x); });
       __syncwarp();
-      sel_fft1024_fwd(v, sc.g, tw, lane);   // IFFT(G) = swap(FFT(swap(G))); G itself is the exchange tile
+      warp_fft1024_fwd(v, sc.g, tw, lane);   // IFFT(G) = swap(FFT(swap(G))); G itself is the exchange tile
       float* o0 = p.out + (size_t)s * p.out_stream_stride + (size_t)tp * H;
       // one inf/NaN bin makes the reference's whole inverse frame NaN; the two frames of a pair share one complex
       // transform here, so a poisoned frame was zeroed in B3 and is re-poisoned now without touching its partner

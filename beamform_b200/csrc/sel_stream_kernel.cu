@@ -116,30 +116,6 @@ __device__ __forceinline__ void ss_publish(int slot) {
 }
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 
-// forward 1024-point FFT (same compact form as das_kernel.cu); `after_exchange` runs once the exchange tile is free again
-template <class F>
-__device__ __forceinline__ void ss_fft1024_fwd(float2 (&v)[32], float2* tile, const float2* __restrict__ tw, int lane, F&& after_exchange) {
-#pragma unroll 1
-  for (int pass = 0; pass < 2; pass++) {
-    fft_dit<32, -1>(v);
-    if (pass == 0) {
-#pragma unroll
-      for (int k1 = 1; k1 < 32; k1++) v[k1] = cmul(v[k1], tw[k1 * 32 + lane]);
-#pragma unroll
-      for (int k1 = 0; k1 < 32; k1++) tile[k1 * 32 + (lane ^ ((k1 & 15) << 1))] = v[k1];
-      __syncwarp();
-      const float4* row = reinterpret_cast<const float4*>(tile + lane * 32);
-      const int sw = lane & 15;
-      static_for<0, 16>([&](auto q) {
-        const float4 r = row[q ^ sw];
-        v[brev5(2 * q)] = make_float2(r.x, r.y);
-        v[brev5(2 * q + 1)] = make_float2(r.z, r.w);
-      });
-      __syncwarp();
-      after_exchange();
-    }
-  }
-}
 
 __device__ __noinline__ bool ss_gate_fp64(const KernelParams& p, int s, int t, int l, int f, int lane) { return gate_fp64(p, s, t, l, f, lane); }
 
@@ -416,7 +392,7 @@ __global__ void __launch_bounds__(SsCfg<ALGO>::kThreads, 1) sel_stream_kernel(co
         }
       }
       // ------------------------------------------------------------------ the transform (one code copy for both roles)
-      ss_fft1024_fwd(v, tile, sh.tw, lane, [&]() {
+      warp_fft1024_fwd(v, tile, sh.tw, lane, [&]() {
         // the exchange tile is free until the next pair: its hops start to arrive now, behind the second FFT pass,
         // the gate and the staging of this pair
         if (have && use_tma && lane == 0 && (ip + 1 < npairs || s + (int)gridDim.x < s_end)) {

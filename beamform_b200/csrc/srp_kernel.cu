@@ -22,27 +22,6 @@ namespace bf {
 constexpr int kSrpL = 514;   // logical bins of a 1024-point frame
 constexpr int kSrpTilePitch = 1026;   // float2 per warp tile in srp_spectra_kernel
 
-__device__ __forceinline__ void srp_fft1024_fwd(float2 (&v)[32], float2* tile, const float2* __restrict__ tw, int lane) {
-#pragma unroll 1
-  for (int pass = 0; pass < 2; pass++) {
-    fft_dit<32, -1>(v);
-    if (pass == 0) {
-#pragma unroll
-      for (int k1 = 1; k1 < 32; k1++) v[k1] = cmul(v[k1], tw[k1 * 32 + lane]);
-#pragma unroll
-      for (int k1 = 0; k1 < 32; k1++) tile[k1 * 32 + (lane ^ ((k1 & 15) << 1))] = v[k1];
-      __syncwarp();
-      const float4* row = reinterpret_cast<const float4*>(tile + lane * 32);
-      const int sw = lane & 15;
-      static_for<0, 16>([&](auto q) {
-        const float4 r = row[q ^ sw];
-        v[brev5(2 * q)] = make_float2(r.x, r.y);
-        v[brev5(2 * q + 1)] = make_float2(r.z, r.w);
-      });
-      __syncwarp();
-    }
-  }
-}
 
 // grid = (pairs, streams); frame index f = s*n_hops + t
 __global__ void __launch_bounds__(256, 1) srp_spectra_kernel(const KernelParams p, unsigned char* __restrict__ xi, int n_hops, size_t image_bytes, size_t lbo) {
@@ -86,7 +65,7 @@ __global__ void __launch_bounds__(256, 1) srp_spectra_kernel(const KernelParams 
         v[brev5(r)] = make_float2(a * w0, bb * w0);
         v[brev5(r + 16)] = make_float2(bb * w1, c * w1);
       });
-      srp_fft1024_fwd(v, tile, tw, lane);
+      warp_fft1024_fwd(v, tile, tw, lane);
 #pragma unroll
       for (int k2 = 0; k2 < 32; k2++) tile[k2 * 32 + lane] = v[k2];
     }

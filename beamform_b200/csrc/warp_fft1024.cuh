@@ -53,6 +53,40 @@ __device__ __forceinline__ void warp_fft1024(float2 (&v)[32], float2* tile, cons
   fft_dit<32, DIR>(v);
 }
 
+// The transform the 1024-point kernels of rounds 1-2 use (das_pairs, sel_pairs, sel_stream, mcra_pairs, srp_spectra): forward only,
+// with an 8 KB XOR-swizzled exchange tile.  Element (row k1, col c) lives at float2 index k1*32 + (c ^ ((k1 & 15) << 1)): row stores are
+// full 256-byte rows, column loads are LDS.128 whose eight lanes per phase fall into distinct 16-byte bank groups (no padding).
+// The two 32-point register passes share ONE copy of the butterfly code (rolled 2-trip loop), so that a kernel's hot loop fits the
+// instruction caches; the inverse reuses it through IFFT(x) = swap(FFT(swap(x))), swap = exchange of real and imaginary parts.
+// `after_exchange` runs once the exchange step has read the tile: the tile is free from there on (the caller may start a TMA copy
+// of the next job's hops into it).
+template <class F>
+__device__ __forceinline__ void warp_fft1024_fwd(float2 (&v)[32], float2* tile, const float2* __restrict__ tw, int lane, F&& after_exchange) {
+#pragma unroll 1
+  for (int pass = 0; pass < 2; pass++) {
+    fft_dit<32, -1>(v);
+    if (pass == 0) {
+#pragma unroll
+      for (int k1 = 1; k1 < 32; k1++) v[k1] = cmul(v[k1], tw[k1 * 32 + lane]);
+#pragma unroll
+      for (int k1 = 0; k1 < 32; k1++) tile[k1 * 32 + (lane ^ ((k1 & 15) << 1))] = v[k1];
+      __syncwarp();
+      const float4* row = reinterpret_cast<const float4*>(tile + lane * 32);
+      const int sw = lane & 15;
+      static_for<0, 16>([&](auto q) {
+        const float4 r = row[q ^ sw];
+        v[brev5(2 * q)] = make_float2(r.x, r.y);
+        v[brev5(2 * q + 1)] = make_float2(r.z, r.w);
+      });
+      __syncwarp();
+      after_exchange();
+    }
+  }
+}
+__device__ __forceinline__ void warp_fft1024_fwd(float2 (&v)[32], float2* tile, const float2* __restrict__ tw, int lane) {
+  warp_fft1024_fwd(v, tile, tw, lane, [] {});
+}
+
 // sqrt-Hann window (util.h:201-211: sqrt(0.5 - 0.5 cos(2 pi n/N)) = sin(pi n/N) for 0 <= n < N) at
 // n = 32*r + lane, built from the lane's (sin, cos)(pi*lane/N) and compile-time (cos, sin)(pi*r/32):
 // two full-rate FP32 instructions, no table traffic.
